@@ -1,0 +1,51 @@
+// avs_bwd_kernel.cuh — reverse-sweep (BPTT) kernel template (instantiated in avs_k_bwd_*.cu)
+//
+// rollout_bwd_kernel replaces the CppAD tape + ADFun::Reverse(1) of Trainer::trainTrajectory
+// (/root/reference/src/Trainer.cpp:607-657).  Per RK4 step it reloads the four stage records the forward
+// sweep stored (coalesced, 448 B per vehicle-step), recomputes each stage's tire-network activations in
+// registers and immediately back-propagates through them.  dL/dW is accumulated per lane in a private
+// shared-memory column ([104][kBwdBlock] doubles, conflict-free: consecutive lanes -> consecutive banks),
+// summed over the lanes of a vehicle at the end and written as the per-sample gradient gps[104][N].
+#pragma once
+#include "avs_kernels.h"
+
+namespace avs {
+
+struct SmemAcc {
+    double* col;  // &smem[threadIdx.x]; element k lives at col[k * kBwdBlock]
+    __device__ __forceinline__ void add(int k, double v) { col[k * kBwdBlock] += v; }
+};
+
+template <int TERR>
+__global__ void __launch_bounds__(kBwdBlock) rollout_bwd_kernel(const __grid_constant__ ModelConst mc, const __grid_constant__ RolloutArgs a) {
+    extern __shared__ double smem[];
+        const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    int n = gid >> 2;
+    const int lane0 = gid & 3;
+    const bool valid = n < a.Nc;
+    if (!valid) n = a.Nc - 1;
+    SmemAcc acc{smem + threadIdx.x};
+#pragma unroll 8
+    for (int k = 0; k < kNumLive; k++) acc.col[k * kBwdBlock] = 0.0;
+    double loss;
+    rollout_bwd_body<1, TERR>(mc, a, n, lane0, acc, loss);
+    const bool writer = valid && lane0 == 0;
+    for (int k = 0; k < kNumLive; k++) {
+        const double g = Group<1>::sum(acc.col[k * kBwdBlock]);
+        if (writer) a.gps[(size_t)k * a.N + n] = g;
+    }
+    if (writer) a.loss[n] = loss;
+}
+
+
+template <int TERR> static cudaError_t launch_bwd_t(const ModelConst& mc, const RolloutArgs& a, cudaStream_t s) {
+    const long long threads = (long long)a.Nc * 4;
+    const int grid = (int)((threads + kBwdBlock - 1) / kBwdBlock);
+    const size_t smem = (size_t)kNumLive * kBwdBlock * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(rollout_bwd_kernel<TERR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    rollout_bwd_kernel<TERR><<<grid, kBwdBlock, smem, s>>>(mc, a);
+    return cudaGetLastError();
+}
+
+}  // namespace avs

@@ -1,0 +1,804 @@
+// avs_model.cuh — constant-folded Jackal vehicle ODE, RK4 step and their hand-written adjoints.
+//
+// This is the arithmetic core of the sm_100a kernels (avs_kernels.cu).  It is written as
+// __host__ __device__ templates so that the *same* source is also compiled by g++ into the CPU
+// unit-test harness tests/hostcheck (which checks it against oracle/ without a GPU).  It is NOT a
+// CPU fallback: the shipped library (libavsim.so) only reaches it through CUDA kernels.
+//
+// What the reference does per ODE call (all on CppAD::AD<double>, dense 6x6 Eigen products) and how
+// it is folded here — reference paths relative to /root/reference:
+//   * joint angles are frozen at q = 0 (src/auvsl_dynamics/HybridDynamics.cpp:520) so the four wheel
+//     motion transforms X_i (generated/transforms.cpp:194-239, 286-331, 378-423, 470-515) are the
+//     constant matrices [[E,0],[-E t_i^, E]],  E = [[1,0,0],[0,0,-1],[0,1,0]]
+//   * the articulated inertia of a wheel, Ia = I_w - U U^T / D (generated/forward_dynamics.cpp:116),
+//     and the assembled base inertia AI_b = I_b + sum_i X_i^T Ia X_i (:118-153) are constants; the
+//     LLT solve of :156 becomes a product with the precomputed inverse (ModelConst::AIinv)
+//   * the third ABA pass (:158-173) only produces qdd, which the caller discards
+//     (HybridDynamics.cpp:627-630) — dropped
+//   * TireNetwork::forward (src/auvsl_dynamics/TireNetwork.cpp:54-119) always uses network 0
+//     (HybridDynamics.cpp:387)
+// Differentiable state ("St", 13 doubles): quaternion x,y,z,w | position | body angular vel | body
+// linear vel  = reference state entries 0-3, 4-6, 11-13, 14-16 (HybridDynamics.h:65-69).  Joint
+// positions (7-10) integrate the controls and feed nothing; joint velocities (17-20) are the controls.
+//
+// Work split ("lanes"): a vehicle is processed by 4/WPT threads, each owning WPT wheels.  Per-wheel
+// work (contact geometry, tire model, ABA passes 1-2 for that wheel) is lane-local; the 6-vector
+// bias-force contributions are summed across the lanes of the group (Group<WPT>::sum, warp shuffles
+// on the device, identity when WPT == 4) and the small base-link part is evaluated redundantly.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define AVS_HD __host__ __device__ __forceinline__
+#else
+#define AVS_HD inline
+#endif
+
+namespace avs {
+
+// ------------------------------------------------------------------------------------------------
+// Model constants (generated/model_constants.h:24-100); see DESIGN.md §3 for the derivations
+// ------------------------------------------------------------------------------------------------
+constexpr double kTireRadius = .098;
+constexpr double kTx = 0.13099999725818634;   // |tx| of the wheel joints; FL,FR = +, RL,RR = -
+constexpr double kTy = 0.1877949982881546;    // |ty|; FL,RL = +, FR,RR = -
+constexpr double kTz = 0.03449999913573265;
+constexpr double kRz = kTz + (-kTireRadius);  // contact point z offset (HybridDynamics.cpp:222-232)
+constexpr double kMb = 16.52400016784668;
+constexpr double kCx = 0.011999273672699928, kCz = 0.06699594855308533;  // base COM (comy forced to 0, :50,:68)
+constexpr double kIbxx = 0.38783785700798035, kIbyy = 0.46875107288360596, kIbzz = 0.4509454071521759;
+constexpr double kIbxy = 0.0011965520679950714, kIbxz = -0.003115505911409855, kIbyz = 0.0031140821520239115;
+constexpr double kMw = 0.47699999809265137;
+constexpr double kIwxx = 0.0013000000035390258, kIwyy = 0.0013000000035390258, kIwzz = 0.002400000113993883;
+constexpr double kIwyz = 4.808253448174149E-11;
+constexpr double kIwyyA = kIwyy - kIwyz * kIwyz / kIwzz;  // Ia(AY,AY) after compute_Ia_revolute
+constexpr double kKappa = kIwyz / kIwzz;                  // -U(AY)/D
+constexpr double kGravity = -9.81;                        // HybridDynamics.cpp:34
+constexpr double kDt = 1e-3;                              // HybridDynamics.cpp:33
+// TireNetwork scalers (TireNetwork.cpp:11-13)
+constexpr double kOutStd0 = 17.241097080572587, kOutStd1 = 15.9103406661298, kOutStd2 = 12.632573461434308;
+constexpr double kInStd0 = 0.0008373582968488336, kInStd1 = 0.5799984931945801, kInStd2 = 0.576934278011322,
+                 kInStd3 = 0.5774632096290588;
+constexpr double kNNDamp = -20.0;       // HybridDynamics.cpp:403
+constexpr double kBekkerDamp = -200.0;  // BekkerDynamics.cpp:106
+
+enum TireKind { TIRE_NN = 0, TIRE_BEKKER = 1 };
+enum TerrainKind { TERR_FLAT = 0, TERR_SLOPE = 1, TERR_BUMPY = 2, TERR_GRID = 3, TERR_DYN = 7 /* switch on ModelConst::terr_kind at run time */ };
+
+constexpr int kNumNNParams = 416;  // TireNetwork::getNumParams (TireNetwork.cpp:122-128): 4 nets x 104
+constexpr int kNumLive = 104;      // only net 0 is evaluated -> entries 104..415 of the gradient are 0
+constexpr int kOffW0 = 0, kOffW2 = 24, kOffW4 = 88;  // pack order W0,W2,W4 row-major (TireNetwork.cpp:130-161)
+
+struct GridTerrain {
+    const double* height;  // [ny][nx]
+    const double* soil;    // [5][ny][nx] or nullptr
+    int nx, ny;
+    double x0, y0, inv_dx, inv_dy;
+};
+
+// Everything a kernel needs besides per-vehicle data; passed by value (__grid_constant__), so every
+// entry is a constant-bank operand with a compile-time offset.
+struct ModelConst {
+    double W0[8][3], W2[8][8], W4[2][8];  // trainable xy-net (TireNetwork.h:40-42)
+    double Z0[8], Z2[8][8], Z4[8];        // fixed z-net (TireNetwork.cpp:17-32)
+    double AIinv[6][6];                   // (I_b + sum X^T Ia X)^-1
+    double bek[5];                        // Bekker soil 5-vector as passed to setParams (BekkerDynamics.cpp:12-21)
+    GridTerrain grid;
+    int terr_kind;                        // used by the TERR_DYN instantiations
+};
+
+// ------------------------------------------------------------------------------------------------
+// fp64 tanh.  tanh|x| = (1-e)/(1+e), e = exp(-2|x|): one exp (Cody-Waite reduction + degree-11
+// polynomial, |rel err| < 2e-17 before rounding) and one division on d in [1,2] (hardware
+// reciprocal seed + cubic Newton step + one residual correction).  Absolute error <= ~2e-16.
+// ------------------------------------------------------------------------------------------------
+AVS_HD double exp_negarg(double x /* <= 0 */) {
+    const double L2E = 1.4426950408889634e+0, MAGIC = 6755399441055744.0;
+    const double LN2_HI = 6.93147180559945286e-01, LN2_LO = 2.31904681384629956e-17;
+    double t = fma(x, L2E, MAGIC);
+    double kd = t - MAGIC;
+    double r = fma(kd, -LN2_HI, x);
+    r = fma(kd, -LN2_LO, r);
+    double p = 2.5110049204818658e-08;
+    p = fma(p, r, 2.763265472252779e-07);
+    p = fma(p, r, 2.755724088722987e-06);
+    p = fma(p, r, 2.4801485441561313e-05);
+    p = fma(p, r, 0.00019841269890076403);
+    p = fma(p, r, 0.0013888888952352863);
+    p = fma(p, r, 0.008333333333319589);
+    p = fma(p, r, 0.04166666666648795);
+    p = fma(p, r, 0.1666666666666668);
+    p = fma(p, r, 0.5000000000000019);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+#if defined(__CUDA_ARCH__)
+    int k = __double2loint(t);
+    k = max(k, -1000);  // exp(-693) ~ 1e-301: result irrelevant next to 1, keeps the exponent field valid
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+#else
+    int64_t k = (int64_t)kd;
+    if (k < -1000) k = -1000;
+    return ldexp(p, (int)k);
+#endif
+}
+
+AVS_HD double div_1to2(double n, double d /* in [1,2] */) {
+#if defined(__CUDA_ARCH__)
+    double r0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(d));
+    double e0 = fma(-d, r0, 1.0);
+    double e1 = fma(e0, e0, e0);
+    double r1 = fma(r0, e1, r0);
+    double q = n * r1;
+    double rem = fma(-d, q, n);
+    return fma(rem, r1, q);
+#else
+    return n / d;
+#endif
+}
+
+AVS_HD double tanh_f64(double x) {
+    double ax = fabs(x);
+    double e = exp_negarg(-2.0 * ax);
+    double t = div_1to2(1.0 - e, 1.0 + e);
+    return copysign(t, x);
+}
+
+AVS_HD double rsqrt_f64(double x) {  // for quaternion re-normalisation, x ~ 1
+#if defined(__CUDA_ARCH__)
+    return rsqrt(x);
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// Lane group
+// ------------------------------------------------------------------------------------------------
+template <int WPT> struct Group {
+    static_assert(WPT == 1 || WPT == 2 || WPT == 4, "wheels per thread");
+    static constexpr int LANES = 4 / WPT;
+    // sum over the lanes of the group; every lane receives the total
+    AVS_HD static double sum(double x) {
+#if defined(__CUDA_ARCH__)
+        if (WPT <= 2) x += __shfl_xor_sync(0xffffffffu, x, 1);
+        if (WPT == 1) x += __shfl_xor_sync(0xffffffffu, x, 2);
+#endif
+        return x;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Terrain lookup: altitude and its gradient at (x, y)
+//   (src/types/TerrainMap.h:10, src/TestTerrainMaps.cpp:6-28; grid = extension)
+// ------------------------------------------------------------------------------------------------
+struct GridCellD { int i, j; double fu, fv, du, dv; };  // du/dv: d(fu)/dx, d(fv)/dy (0 where clamped)
+AVS_HD GridCellD grid_cell(const GridTerrain& g, double x, double y) {
+    double u = (x - g.x0) * g.inv_dx, v = (y - g.y0) * g.inv_dy;
+    const double umax = (double)(g.nx - 1), vmax = (double)(g.ny - 1);
+    GridCellD c;
+    c.du = g.inv_dx; c.dv = g.inv_dy;
+    if (u < 0.0) { u = 0.0; c.du = 0.0; }
+    if (u > umax) { u = umax; c.du = 0.0; }
+    if (v < 0.0) { v = 0.0; c.dv = 0.0; }
+    if (v > vmax) { v = vmax; c.dv = 0.0; }
+    int i = (int)floor(u), j = (int)floor(v);
+    i = i > g.nx - 2 ? g.nx - 2 : i; j = j > g.ny - 2 ? g.ny - 2 : j;
+    i = i < 0 ? 0 : i; j = j < 0 ? 0 : j;
+    c.i = i; c.j = j; c.fu = u - (double)i; c.fv = v - (double)j;
+    return c;
+}
+AVS_HD double grid_lerp(const GridTerrain& g, const double* f, const GridCellD& c, double* dfdx, double* dfdy) {
+    const double* row0 = f + (size_t)c.j * g.nx + c.i;
+    const double* row1 = row0 + g.nx;
+#if defined(__CUDA_ARCH__)
+    const double h00 = __ldg(row0), h01 = __ldg(row0 + 1), h10 = __ldg(row1), h11 = __ldg(row1 + 1);
+#else
+    const double h00 = row0[0], h01 = row0[1], h10 = row1[0], h11 = row1[1];
+#endif
+    const double a = h00 + c.fu * (h01 - h00);
+    const double b = h10 + c.fu * (h11 - h10);
+    if (dfdx) {
+        *dfdx = ((h01 - h00) + c.fv * ((h11 - h10) - (h01 - h00))) * c.du;
+        *dfdy = (b - a) * c.dv;
+    }
+    return a + c.fv * (b - a);
+}
+
+template <int TERR> AVS_HD double altitude(const ModelConst& mc, double x, double y, double& dax, double& day) {
+    const int kind = (TERR == TERR_DYN) ? mc.terr_kind : TERR;
+    if (kind == TERR_FLAT) { dax = 0.0; day = 0.0; return 0.0; }
+    if (kind == TERR_SLOPE) { dax = 0.1; day = 0.0; return 0.1 * x; }
+    if (kind == TERR_BUMPY) {
+        // CondExpLt(arg,1.6,arg,0); CondExpGt(arg,0,arg,0); temp=.2 sin(arg); CondExpGt(temp,0,temp,0)
+        double arg = x - 2.0;
+        bool live = true;
+        if (!(arg < 1.6)) { arg = 0.0; live = false; }
+        if (!(arg > 0.0)) { arg = 0.0; live = false; }
+        double temp = .2 * sin(arg);
+        day = 0.0;
+        if (temp > 0.0) { dax = live ? .2 * cos(arg) : 0.0; return temp; }
+        dax = 0.0;
+        return 0.0;
+    }
+    GridCellD c = grid_cell(mc.grid, x, y);
+    return grid_lerp(mc.grid, mc.grid.height, c, &dax, &day);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tire network (TireNetwork.cpp:54-119), network 0.  Activations are kept for the adjoint.
+// ------------------------------------------------------------------------------------------------
+struct NNAct {
+    double s1, s2, s3;  // scaled xy features
+    double h0[8], h2[8], g0[8], g2[8];
+    double z4;
+};
+
+// in: contact velocity (vx, vy), wheel speed w, sinkage zr -> (Fx, Fy, Fz) before the damping term
+AVS_HD void tire_nn_fwd(const ModelConst& mc, double vx, double vy, double w, double zr, double F[3], NNAct& a) {
+    const double s0 = zr * (1.0 / kInStd0);
+    a.s1 = (w * kTireRadius - vx) * (1.0 / kInStd1);
+    a.s2 = w * (1.0 / kInStd2);
+    a.s3 = vy * (1.0 / kInStd3);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        a.h0[j] = tanh_f64(fma(mc.W0[j][2], a.s3, fma(mc.W0[j][1], a.s2, mc.W0[j][0] * a.s1)));
+        a.g0[j] = tanh_f64(mc.Z0[j] * s0);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        double sx = mc.W2[j][0] * a.h0[0], sz = mc.Z2[j][0] * a.g0[0];
+#pragma unroll
+        for (int k = 1; k < 8; k++) { sx = fma(mc.W2[j][k], a.h0[k], sx); sz = fma(mc.Z2[j][k], a.g0[k], sz); }
+        a.h2[j] = tanh_f64(sx);
+        a.g2[j] = tanh_f64(sz);
+    }
+    double f0 = mc.W4[0][0] * a.h2[0], f1 = mc.W4[1][0] * a.h2[0], z4 = mc.Z4[0] * a.g2[0];
+#pragma unroll
+    for (int k = 1; k < 8; k++) { f0 = fma(mc.W4[0][k], a.h2[k], f0); f1 = fma(mc.W4[1][k], a.h2[k], f1); z4 = fma(mc.Z4[k], a.g2[k], z4); }
+    a.z4 = z4;
+    F[0] = f0 * kOutStd0;
+    F[1] = f1 * kOutStd1;
+    F[2] = (z4 > 0.0 ? z4 : 0.0) * kOutStd2;  // relu = CondExpGt(x,0,x,0) (TireNetwork.cpp:47-50)
+}
+
+// adjoint: Fbar[3] -> (vx_bar, vy_bar, zr_bar) and dL/dW accumulation through acc.add(k, value)
+template <class Acc>
+AVS_HD void tire_nn_bwd(const ModelConst& mc, const NNAct& a, const double Fbar[3], double& vxb, double& vyb, double& zrb, Acc& acc) {
+    const double o0 = Fbar[0] * kOutStd0, o1 = Fbar[1] * kOutStd1;
+    const double oz = (a.z4 > 0.0) ? Fbar[2] * kOutStd2 : 0.0;  // CondExpGt: derivative 0 at z4 <= 0
+    double d2[8], e2[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        acc.add(kOffW4 + k, o0 * a.h2[k]);
+        acc.add(kOffW4 + 8 + k, o1 * a.h2[k]);
+        const double hb = fma(mc.W4[1][k], o1, mc.W4[0][k] * o0);
+        d2[k] = hb * fma(-a.h2[k], a.h2[k], 1.0);
+        e2[k] = (mc.Z4[k] * oz) * fma(-a.g2[k], a.g2[k], 1.0);
+    }
+    double d0[8], e0[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        double hb = mc.W2[0][k] * d2[0], gb = mc.Z2[0][k] * e2[0];
+#pragma unroll
+        for (int j = 1; j < 8; j++) { hb = fma(mc.W2[j][k], d2[j], hb); gb = fma(mc.Z2[j][k], e2[j], gb); }
+        d0[k] = hb * fma(-a.h0[k], a.h0[k], 1.0);
+        e0[k] = gb * fma(-a.g0[k], a.g0[k], 1.0);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc.add(kOffW2 + j * 8 + k, d2[j] * a.h0[k]);
+    }
+    double s1b = 0.0, s2b = 0.0, s3b = 0.0, s0b = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        acc.add(kOffW0 + j * 3 + 0, d0[j] * a.s1);
+        acc.add(kOffW0 + j * 3 + 1, d0[j] * a.s2);
+        acc.add(kOffW0 + j * 3 + 2, d0[j] * a.s3);
+        s1b = fma(mc.W0[j][0], d0[j], s1b);
+        s3b = fma(mc.W0[j][2], d0[j], s3b);
+        s0b = fma(mc.Z0[j], e0[j], s0b);
+    }
+    (void)s2b;  // wheel speed is a control, not differentiated
+    vxb = -s1b * (1.0 / kInStd1);
+    vyb = s3b * (1.0 / kInStd3);
+    zrb = s0b * (1.0 / kInStd0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Rotation helpers (src/auvsl_dynamics/utils.cpp:45-52, 20-28)
+// ------------------------------------------------------------------------------------------------
+AVS_HD void quat_to_R(const double q[4], double R[9]) {
+    const double x = q[0], y = q[1], z = q[2], w = q[3];
+    R[0] = 1 - 2 * y * y - 2 * z * z; R[1] = 2 * x * y - 2 * w * z;     R[2] = 2 * x * z + 2 * w * y;
+    R[3] = 2 * x * y + 2 * w * z;     R[4] = 1 - 2 * x * x - 2 * z * z; R[5] = 2 * y * z - 2 * w * x;
+    R[6] = 2 * x * z - 2 * w * y;     R[7] = 2 * y * z + 2 * w * x;     R[8] = 1 - 2 * x * x - 2 * y * y;
+}
+AVS_HD void quat_to_R_bwd(const double q[4], const double Rb[9], double qb[4]) {
+    const double x = q[0], y = q[1], z = q[2], w = q[3];
+    const double s01 = Rb[1] + Rb[3], s02 = Rb[2] + Rb[6], s12 = Rb[5] + Rb[7];
+    const double a01 = Rb[3] - Rb[1], a02 = Rb[2] - Rb[6], a12 = Rb[7] - Rb[5];
+    qb[0] += 2.0 * (y * s01 + z * s02 - 2.0 * x * (Rb[4] + Rb[8]) + w * a12);
+    qb[1] += 2.0 * (x * s01 + z * s12 - 2.0 * y * (Rb[0] + Rb[8]) + w * a02);
+    qb[2] += 2.0 * (x * s02 + y * s12 - 2.0 * z * (Rb[0] + Rb[4]) + w * a01);
+    qb[3] += 2.0 * (z * a01 + y * a02 + x * a12);
+}
+
+// ------------------------------------------------------------------------------------------------
+// One wheel: contact geometry -> tire force -> ABA passes 1 and 2 -> contribution X_i^T pa_i to the
+// base bias force.  (HybridDynamics.cpp:214-253, 321-417; generated/forward_dynamics.cpp:56-153)
+// ------------------------------------------------------------------------------------------------
+struct WheelAct {
+    NNAct nn;
+    double dax, day;          // terrain gradient at the contact point
+    double w0, w1, w2;        // wheel-frame angular velocity (with qd on the joint axis)
+    double u0, u1, u2;        // wheel-frame linear velocity
+    double n0, n1, n2;        // I_w * omega_w
+};
+
+struct NullAcc { AVS_HD void add(int, double) {} };
+
+// wheel index i: 0 FL(+,+) 1 FR(+,-) 2 RL(-,+) 3 RR(-,-); qd = commanded wheel speed
+template <int TERR>
+AVS_HD void wheel_contact(const ModelConst& mc, double tx, double ty, const double R[9], const double X[13], double& sink, double cv[3],
+                          double& dax, double& day, double cp[3]) {
+    const double* p = X + 4; const double* w = X + 7; const double* v = X + 10;
+    cp[0] = fma(R[0], tx, fma(R[1], ty, fma(R[2], kRz, p[0])));
+    cp[1] = fma(R[3], tx, fma(R[4], ty, fma(R[5], kRz, p[1])));
+    cp[2] = fma(R[6], tx, fma(R[7], ty, fma(R[8], kRz, p[2])));
+    const double alt = altitude<TERR>(mc, cp[0], cp[1], dax, day);
+    sink = alt - cp[2];
+    // cv = v - r^ w = v + w x r       (HybridDynamics.cpp:336-346)
+    cv[0] = v[0] + (w[1] * kRz - w[2] * ty);
+    cv[1] = v[1] + (w[2] * tx - w[0] * kRz);
+    cv[2] = v[2] + (w[0] * ty - w[1] * tx);
+}
+
+// ABA passes 1-2 for one wheel given the tire force (Fx, Fy, Fz) in the contact frame
+AVS_HD void wheel_aba_fwd(double tx, double ty, const double X[13], double qd, const double F[3], double C[6], WheelAct& a) {
+    const double* w = X + 7; const double* v = X + 10;
+    // a = v + w x t ; omega_w = E w + qd z ; v_w = E a       (forward_dynamics.cpp:58-59)
+    const double ax = v[0] + (w[1] * kTz - w[2] * ty);
+    const double ay = v[1] + (w[2] * tx - w[0] * kTz);
+    const double az = v[2] + (w[0] * ty - w[1] * tx);
+    a.w0 = w[0]; a.w1 = -w[2]; a.w2 = w[1] + qd;
+    a.u0 = ax;   a.u1 = -az;   a.u2 = ay;
+    // c = crm(v_i)[:,AZ] * qd   (:62-63)
+    const double c0 = qd * a.w1, c1 = -qd * a.w0, c3 = qd * a.u1, c4 = -qd * a.u0;
+    // p = v x* (I v) - fext     (:66, :43)   wheel inertia: com = 0, Ixy = Ixz = 0
+    a.n0 = kIwxx * a.w0;
+    a.n1 = kIwyy * a.w1 - kIwyz * a.w2;
+    a.n2 = kIwzz * a.w2 - kIwyz * a.w1;
+    const double pA0 = a.w1 * a.n2 - a.w2 * a.n1;
+    const double pA1 = a.w2 * a.n0 - a.w0 * a.n2;
+    const double pA2 = a.w0 * a.n1 - a.w1 * a.n0;
+    // fext (link frame) = (0,0,0, Fx, -Fz, Fy)   (HybridDynamics.cpp:405-411)
+    const double pL0 = kMw * (a.w1 * a.u2 - a.w2 * a.u1) - F[0];
+    const double pL1 = kMw * (a.w2 * a.u0 - a.w0 * a.u2) + F[2];
+    const double pL2 = kMw * (a.w0 * a.u1 - a.w1 * a.u0) - F[1];
+    // pa = p + Ia c + U u / D,  u = -p[AZ]     (:112-117)
+    const double pa0 = fma(kIwxx, c0, pA0);
+    const double pa1 = fma(kKappa, pA2, fma(kIwyyA, c1, pA1));
+    const double pa3 = fma(kMw, c3, pL0);
+    const double pa4 = fma(kMw, c4, pL1);
+    const double pa5 = pL2;
+    // X^T pa: force transform to the base frame   (:120)
+    const double fb0 = pa3, fb1 = pa5, fb2 = -pa4;
+    C[0] = pa0 + (ty * fb2 - kTz * fb1);
+    C[1] = (kTz * fb0 - tx * fb2);
+    C[2] = -pa1 + (tx * fb1 - ty * fb0);
+    C[3] = fb0; C[4] = fb1; C[5] = fb2;
+}
+
+// adjoint of wheel_aba_fwd: Cb[6] -> Fb[3] (tire force adjoint) and += into wb[3], vb[3]
+AVS_HD void wheel_aba_bwd(double tx, double ty, double qd, const WheelAct& a, const double Cb[6], double Fb[3], double wb[3], double vb[3]) {
+    // C = (pa0, 0, -pa1) + t x fb ; fb
+    const double pa0b = Cb[0], pa1b = -Cb[2];
+    // fb_bar = Cb[3..5] + (a x t) with a = Cb[0..2]
+    const double fb0b = Cb[3] + (Cb[1] * kTz - Cb[2] * ty);
+    const double fb1b = Cb[4] + (Cb[2] * tx - Cb[0] * kTz);
+    const double fb2b = Cb[5] + (Cb[0] * ty - Cb[1] * tx);
+    const double pa3b = fb0b, pa5b = fb1b, pa4b = -fb2b;
+    const double pA0b = pa0b, c0b = kIwxx * pa0b;
+    const double pA1b = pa1b, c1b = kIwyyA * pa1b, pA2b = kKappa * pa1b;
+    const double pL0b = pa3b, c3b = kMw * pa3b;
+    const double pL1b = pa4b, c4b = kMw * pa4b;
+    const double pL2b = pa5b;
+    Fb[0] = -pL0b; Fb[2] = pL1b; Fb[1] = -pL2b;
+    // pL = m w x u - ...:  w_bar += m (u x pLb), u_bar += m (pLb x w)
+    double w0b = kMw * (a.u1 * pL2b - a.u2 * pL1b);
+    double w1b = kMw * (a.u2 * pL0b - a.u0 * pL2b);
+    double w2b = kMw * (a.u0 * pL1b - a.u1 * pL0b);
+    double u0b = kMw * (pL1b * a.w2 - pL2b * a.w1);
+    double u1b = kMw * (pL2b * a.w0 - pL0b * a.w2);
+    double u2b = kMw * (pL0b * a.w1 - pL1b * a.w0);
+    // pA = w x n: w_bar += n x pAb ; n_bar = pAb x w
+    w0b += a.n1 * pA2b - a.n2 * pA1b;
+    w1b += a.n2 * pA0b - a.n0 * pA2b;
+    w2b += a.n0 * pA1b - a.n1 * pA0b;
+    const double n0b = pA1b * a.w2 - pA2b * a.w1;
+    const double n1b = pA2b * a.w0 - pA0b * a.w2;
+    const double n2b = pA0b * a.w1 - pA1b * a.w0;
+    // n = I_w w (symmetric)
+    w0b += kIwxx * n0b;
+    w1b += kIwyy * n1b - kIwyz * n2b;
+    w2b += kIwzz * n2b - kIwyz * n1b;
+    // c0 = qd w1, c1 = -qd w0, c3 = qd u1, c4 = -qd u0
+    w1b += qd * c0b; w0b -= qd * c1b; u1b += qd * c3b; u0b -= qd * c4b;
+    // omega_w = (wx, -wz, wy + qd) ; v_w = (ax, -az, ay)
+    wb[0] += w0b; wb[2] -= w1b; wb[1] += w2b;
+    const double axb = u0b, azb = -u1b, ayb = u2b;
+    // a = v + w x t:  v_bar += ab ; w_bar += t x ab
+    vb[0] += axb; vb[1] += ayb; vb[2] += azb;
+    wb[0] += ty * azb - kTz * ayb;
+    wb[1] += kTz * axb - tx * azb;
+    wb[2] += tx * ayb - ty * axb;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Base link: bias force of the base + assembled acceleration + kinematics
+//   (forward_dynamics.cpp:105, 156, 177; HybridDynamics.cpp:561-631)
+// ------------------------------------------------------------------------------------------------
+AVS_HD void base_inertia_mul(const double w[3], const double v[3], double nB[3], double fB[3]) {
+    // n = Ibar w + m c x v ; f = m (v + w x c),  c = (cx, 0, cz)
+    nB[0] = kIbxx * w[0] - kIbxy * w[1] - kIbxz * w[2] + kMb * (0.0 * v[2] - kCz * v[1]);
+    nB[1] = -kIbxy * w[0] + kIbyy * w[1] - kIbyz * w[2] + kMb * (kCz * v[0] - kCx * v[2]);
+    nB[2] = -kIbxz * w[0] - kIbyz * w[1] + kIbzz * w[2] + kMb * (kCx * v[1] - 0.0 * v[0]);
+    fB[0] = kMb * (v[0] + (w[1] * kCz - w[2] * 0.0));
+    fB[1] = kMb * (v[1] + (w[2] * kCx - w[0] * kCz));
+    fB[2] = kMb * (v[2] + (w[0] * 0.0 - w[1] * kCx));
+}
+
+// S = summed wheel contributions; Xd = time derivative of the 13 live states
+AVS_HD void base_fwd(const ModelConst& mc, const double R[9], const double X[13], const double S[6], double Xd[13]) {
+    const double* q = X; const double* w = X + 7; const double* v = X + 10;
+    double nB[3], fB[3], pb[6];
+    base_inertia_mul(w, v, nB, fB);
+    pb[0] = (w[1] * nB[2] - w[2] * nB[1]) + (v[1] * fB[2] - v[2] * fB[1]) + S[0];
+    pb[1] = (w[2] * nB[0] - w[0] * nB[2]) + (v[2] * fB[0] - v[0] * fB[2]) + S[1];
+    pb[2] = (w[0] * nB[1] - w[1] * nB[0]) + (v[0] * fB[1] - v[1] * fB[0]) + S[2];
+    pb[3] = (w[1] * fB[2] - w[2] * fB[1]) + S[3];
+    pb[4] = (w[2] * fB[0] - w[0] * fB[2]) + S[4];
+    pb[5] = (w[0] * fB[1] - w[1] * fB[0]) + S[5];
+    // quaternion rate (utils.cpp:20-28)
+    Xd[0] = .5 * (q[3] * w[0] - q[2] * w[1] + q[1] * w[2]);
+    Xd[1] = .5 * (q[2] * w[0] + q[3] * w[1] - q[0] * w[2]);
+    Xd[2] = .5 * (-q[1] * w[0] + q[0] * w[1] + q[3] * w[2]);
+    Xd[3] = .5 * (-q[0] * w[0] - q[1] * w[1] - q[2] * w[2]);
+    // world-frame linear velocity (HybridDynamics.cpp:604)
+    Xd[4] = R[0] * v[0] + R[1] * v[1] + R[2] * v[2];
+    Xd[5] = R[3] * v[0] + R[4] * v[1] + R[5] * v[2];
+    Xd[6] = R[6] * v[0] + R[7] * v[1] + R[8] * v[2];
+    // a = -AI^-1 p + g_b,  g_b = R^T (0,0,-9.81)
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+        double s = mc.AIinv[r][0] * pb[0];
+#pragma unroll
+        for (int c = 1; c < 6; c++) s = fma(mc.AIinv[r][c], pb[c], s);
+        Xd[7 + r] = -s;
+    }
+    Xd[10] += kGravity * R[6];
+    Xd[11] += kGravity * R[7];
+    Xd[12] += kGravity * R[8];
+}
+
+// adjoint of base_fwd: Xdb[13] -> Sb[6] (= adjoint of every wheel contribution), += Xb[13], += Rb[9]
+AVS_HD void base_bwd(const ModelConst& mc, const double R[9], const double X[13], const double Xdb[13], double Sb[6], double Xb[13], double Rb[9]) {
+    const double* q = X; const double* w = X + 7; const double* v = X + 10;
+    double* qb = Xb; double* wb = Xb + 7; double* vb = Xb + 10;
+    // acceleration rows
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+        double s = mc.AIinv[0][c] * Xdb[7];
+#pragma unroll
+        for (int r = 1; r < 6; r++) s = fma(mc.AIinv[r][c], Xdb[7 + r], s);
+        Sb[c] = -s;
+    }
+    Rb[6] += kGravity * Xdb[10];
+    Rb[7] += kGravity * Xdb[11];
+    Rb[8] += kGravity * Xdb[12];
+    double nB[3], fB[3];
+    base_inertia_mul(w, v, nB, fB);
+    const double* a = Sb; const double* b = Sb + 3;
+    // pb_n = w x nB + v x fB ; pb_f = w x fB
+    double nBb[3], fBb[3];
+    wb[0] += (nB[1] * a[2] - nB[2] * a[1]) + (fB[1] * b[2] - fB[2] * b[1]);
+    wb[1] += (nB[2] * a[0] - nB[0] * a[2]) + (fB[2] * b[0] - fB[0] * b[2]);
+    wb[2] += (nB[0] * a[1] - nB[1] * a[0]) + (fB[0] * b[1] - fB[1] * b[0]);
+    vb[0] += fB[1] * a[2] - fB[2] * a[1];
+    vb[1] += fB[2] * a[0] - fB[0] * a[2];
+    vb[2] += fB[0] * a[1] - fB[1] * a[0];
+    nBb[0] = a[1] * w[2] - a[2] * w[1];
+    nBb[1] = a[2] * w[0] - a[0] * w[2];
+    nBb[2] = a[0] * w[1] - a[1] * w[0];
+    fBb[0] = (a[1] * v[2] - a[2] * v[1]) + (b[1] * w[2] - b[2] * w[1]);
+    fBb[1] = (a[2] * v[0] - a[0] * v[2]) + (b[2] * w[0] - b[0] * w[2]);
+    fBb[2] = (a[0] * v[1] - a[1] * v[0]) + (b[0] * w[1] - b[1] * w[0]);
+    // nB = Ibar w + m c x v  ->  w_bar += Ibar nBb ; v_bar += m (nBb x c)
+    wb[0] += kIbxx * nBb[0] - kIbxy * nBb[1] - kIbxz * nBb[2];
+    wb[1] += -kIbxy * nBb[0] + kIbyy * nBb[1] - kIbyz * nBb[2];
+    wb[2] += -kIbxz * nBb[0] - kIbyz * nBb[1] + kIbzz * nBb[2];
+    vb[0] += kMb * (nBb[1] * kCz - nBb[2] * 0.0);
+    vb[1] += kMb * (nBb[2] * kCx - nBb[0] * kCz);
+    vb[2] += kMb * (nBb[0] * 0.0 - nBb[1] * kCx);
+    // fB = m v + m w x c    ->  v_bar += m fBb ; w_bar += m (c x fBb)
+    vb[0] += kMb * fBb[0]; vb[1] += kMb * fBb[1]; vb[2] += kMb * fBb[2];
+    wb[0] += kMb * (0.0 * fBb[2] - kCz * fBb[1]);
+    wb[1] += kMb * (kCz * fBb[0] - kCx * fBb[2]);
+    wb[2] += kMb * (kCx * fBb[1] - 0.0 * fBb[0]);
+    // quaternion rate
+    const double l0 = .5 * Xdb[0], l1 = .5 * Xdb[1], l2 = .5 * Xdb[2], l3 = .5 * Xdb[3];
+    wb[0] += q[3] * l0 + q[2] * l1 - q[1] * l2 - q[0] * l3;
+    wb[1] += -q[2] * l0 + q[3] * l1 + q[0] * l2 - q[1] * l3;
+    wb[2] += q[1] * l0 - q[0] * l1 + q[3] * l2 - q[2] * l3;
+    qb[0] += -w[2] * l1 + w[1] * l2 - w[0] * l3;
+    qb[1] += w[2] * l0 - w[0] * l2 - w[1] * l3;
+    qb[2] += -w[1] * l0 + w[0] * l1 - w[2] * l3;
+    qb[3] += w[0] * l0 + w[1] * l1 + w[2] * l2;
+    // pdot = R v
+    vb[0] += R[0] * Xdb[4] + R[3] * Xdb[5] + R[6] * Xdb[6];
+    vb[1] += R[1] * Xdb[4] + R[4] * Xdb[5] + R[7] * Xdb[6];
+    vb[2] += R[2] * Xdb[4] + R[5] * Xdb[5] + R[8] * Xdb[6];
+    Rb[0] += Xdb[4] * v[0]; Rb[1] += Xdb[4] * v[1]; Rb[2] += Xdb[4] * v[2];
+    Rb[3] += Xdb[5] * v[0]; Rb[4] += Xdb[5] * v[1]; Rb[5] += Xdb[5] * v[2];
+    Rb[6] += Xdb[6] * v[0]; Rb[7] += Xdb[6] * v[1]; Rb[8] += Xdb[6] * v[2];
+}
+
+}  // namespace avs
+
+#include "avs_bekker.cuh"
+
+namespace avs {
+
+AVS_HD void wheel_sign(int i, double& tx, double& ty) {
+    tx = (i & 2) ? -kTx : kTx;
+    ty = (i & 1) ? -kTy : kTy;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Full ODE:  Xd = f(X; u)      (HybridDynamics::ODE, HybridDynamics.cpp:519-631)
+//   lane0 = first wheel owned by this thread; ul, ur = commanded left / right wheel speeds
+// ------------------------------------------------------------------------------------------------
+template <int WPT, int TIRE, int TERR>
+AVS_HD void ode_fwd(const ModelConst& mc, int lane0, const double X[13], double ul, double ur, double Xd[13]) {
+    double R[9];
+    quat_to_R(X, R);
+    double S[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < WPT; k++) {
+        const int i = lane0 + k;
+        double tx, ty;
+        wheel_sign(i, tx, ty);
+        const double qd = (i & 1) ? ur : ul;  // qd = (vl, vr, vl, vr)  (HybridDynamics.cpp:539-542)
+        double sink, cv[3], dax, day, cp[3], F[3], C[6];
+        WheelAct act;
+        wheel_contact<TERR>(mc, tx, ty, R, X, sink, cv, dax, day, cp);
+        if (TIRE == TIRE_NN) {
+            tire_nn_fwd(mc, cv[0], cv[1], qd, sink, F, act.nn);
+            F[2] = fma(kNNDamp, cv[2], F[2]);
+        } else {
+            bekker_tire_fwd<TERR>(mc, cv[0], cv[1], qd, sink, cp, F);
+            F[2] = fma(kBekkerDamp, cv[2], F[2]);
+        }
+        wheel_aba_fwd(tx, ty, X, qd, F, C, act);
+#pragma unroll
+        for (int c = 0; c < 6; c++) S[c] += C[c];
+    }
+#pragma unroll
+    for (int c = 0; c < 6; c++) S[c] = Group<WPT>::sum(S[c]);
+    base_fwd(mc, R, X, S, Xd);
+}
+
+// Adjoint of the ODE at stage input X:  Xb += (df/dX)^T Xdb ; weight gradients into acc.
+// The wheel forward is recomputed here so that its activations never leave registers.
+template <int WPT, int TERR, class Acc>
+AVS_HD void ode_bwd_nn(const ModelConst& mc, int lane0, const double X[13], double ul, double ur, const double Xdb[13], double Xb[13], Acc& acc) {
+    double R[9];
+    quat_to_R(X, R);
+    double Sb[6], Rb[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    base_bwd(mc, R, X, Xdb, Sb, Xb, Rb);
+    // wheel-local adjoints, summed over the group: cp_bar (x) r  ->  Rb, pb ; wb ; vb
+    double gx[3] = {0, 0, 0}, gy[3] = {0, 0, 0}, gs[3] = {0, 0, 0};  // sum sx*cpb, sum sy*cpb, sum cpb
+    double wb[3] = {0, 0, 0}, vb[3] = {0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < WPT; k++) {
+        const int i = lane0 + k;
+        double tx, ty;
+        wheel_sign(i, tx, ty);
+        const double qd = (i & 1) ? ur : ul;
+        double sink, cv[3], dax, day, cp[3], F[3], C[6], Fb[3];
+        WheelAct act;
+        wheel_contact<TERR>(mc, tx, ty, R, X, sink, cv, dax, day, cp);
+        tire_nn_fwd(mc, cv[0], cv[1], qd, sink, F, act.nn);
+        F[2] = fma(kNNDamp, cv[2], F[2]);
+        wheel_aba_fwd(tx, ty, X, qd, F, C, act);
+        wheel_aba_bwd(tx, ty, qd, act, Sb, Fb, wb, vb);
+        double cvb[3], sinkb;
+        cvb[2] = kNNDamp * Fb[2];
+        tire_nn_bwd(mc, act.nn, Fb, cvb[0], cvb[1], sinkb, acc);
+        // cv = v + w x r
+        vb[0] += cvb[0]; vb[1] += cvb[1]; vb[2] += cvb[2];
+        wb[0] += ty * cvb[2] - kRz * cvb[1];
+        wb[1] += kRz * cvb[0] - tx * cvb[2];
+        wb[2] += tx * cvb[1] - ty * cvb[0];
+        // sink = alt(cpx, cpy) - cpz
+        const double cpb0 = sinkb * dax, cpb1 = sinkb * day, cpb2 = -sinkb;
+        const double sx = (i & 2) ? -1.0 : 1.0, sy = (i & 1) ? -1.0 : 1.0;
+        gx[0] += sx * cpb0; gx[1] += sx * cpb1; gx[2] += sx * cpb2;
+        gy[0] += sy * cpb0; gy[1] += sy * cpb1; gy[2] += sy * cpb2;
+        gs[0] += cpb0; gs[1] += cpb1; gs[2] += cpb2;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        gx[c] = Group<WPT>::sum(gx[c]); gy[c] = Group<WPT>::sum(gy[c]); gs[c] = Group<WPT>::sum(gs[c]);
+        wb[c] = Group<WPT>::sum(wb[c]); vb[c] = Group<WPT>::sum(vb[c]);
+    }
+    // cp = R r + p with r = (sx*kTx, sy*kTy, kRz)
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        Rb[3 * c + 0] = fma(kTx, gx[c], Rb[3 * c + 0]);
+        Rb[3 * c + 1] = fma(kTy, gy[c], Rb[3 * c + 1]);
+        Rb[3 * c + 2] = fma(kRz, gs[c], Rb[3 * c + 2]);
+        Xb[4 + c] += gs[c];
+        Xb[7 + c] += wb[c];
+        Xb[10 + c] += vb[c];
+    }
+    quat_to_R_bwd(X, Rb, Xb);
+}
+
+// ------------------------------------------------------------------------------------------------
+// RK4 step with per-stage quaternion re-normalisation (HybridDynamics::RK4, HybridDynamics.cpp:461-502)
+// ------------------------------------------------------------------------------------------------
+AVS_HD void renorm(double Y[13], double& inv_norm) {
+    inv_norm = rsqrt_f64(Y[0] * Y[0] + Y[1] * Y[1] + Y[2] * Y[2] + Y[3] * Y[3]);
+    Y[0] *= inv_norm; Y[1] *= inv_norm; Y[2] *= inv_norm; Y[3] *= inv_norm;
+}
+// X = Y/|Y| on the quaternion part: Yb = (Xb - X (X.Xb)) / |Y|, in place
+AVS_HD void renorm_bwd(const double Xn[13], double inv_norm, double Xb[13]) {
+    const double d = Xn[0] * Xb[0] + Xn[1] * Xb[1] + Xn[2] * Xb[2] + Xn[3] * Xb[3];
+#pragma unroll
+    for (int c = 0; c < 4; c++) Xb[c] = (Xb[c] - Xn[c] * d) * inv_norm;
+}
+
+// Stage sink: receives every (normalised) stage input and the inverse norm that produced it
+// (stage 0: the inverse norm of the step OUTPUT, delivered by finish()).  NullSink for plain rollouts.
+struct NullSink {
+    AVS_HD void stage(int, const double*, double) {}
+    AVS_HD void finish(double) {}
+};
+
+// The four stages run as a rolled loop (one copy of the ODE in the instruction stream, registers sized
+// for a single evaluation); the stage weights of HybridDynamics.cpp:470-495 are selected by index.
+template <int WPT, int TIRE, int TERR, class Sink>
+AVS_HD void rk4_fwd(const ModelConst& mc, int lane0, const double X[13], double ul, double ur, double Xn[13], Sink& sink) {
+    double k[13], acc[13], T[13], inv = 1.0;
+    const double h = kDt;
+#pragma unroll
+    for (int c = 0; c < 13; c++) { acc[c] = 0.0; T[c] = X[c]; }
+#pragma unroll 1
+    for (int s = 0; s < 4; s++) {
+        sink.stage(s, T, inv);
+        ode_fwd<WPT, TIRE, TERR>(mc, lane0, T, ul, ur, k);
+        const double wgt = (s == 0 || s == 3) ? 1.0 : 2.0;   // k1 + 2 k2 + 2 k3 + k4
+        const double cs = (s == 2) ? h : .5 * h;             // X + .5h k1, X + .5h k2, X + h k3
+#pragma unroll
+        for (int c = 0; c < 13; c++) { acc[c] = fma(wgt, k[c], acc[c]); T[c] = fma(cs, k[c], X[c]); }
+        renorm(T, inv);
+    }
+#pragma unroll
+    for (int c = 0; c < 13; c++) Xn[c] = fma(h / 6.0, acc[c], X[c]);
+    renorm(Xn, inv);
+    sink.finish(inv);
+}
+
+// Adjoint of one RK4 step.  src.load(s, St, inv) returns stage input s and the inverse norm stored with it
+// (for s = 0: the inverse norm of the step output); Xn = the step's (normalised) output;
+// lam (in/out) = adjoint of Xn on entry, adjoint of the step input on return.
+template <int WPT, int TERR, class Src, class Acc>
+AVS_HD void rk4_bwd_nn(const ModelConst& mc, int lane0, Src& src, const double Xn[13], double ul, double ur, double lam[13], Acc& acc) {
+    const double h = kDt;
+    double Yb[13], Xb[13], kb[13], St[13], inv_s;
+    src.load(0, St, inv_s);  // only inv_s (norm of the step output) is needed before the stage loop
+#pragma unroll
+    for (int c = 0; c < 13; c++) Yb[c] = lam[c];
+    renorm_bwd(Xn, inv_s, Yb);  // adjoint of Y+ = X + h/6 (k1 + 2k2 + 2k3 + k4)
+#pragma unroll
+    for (int c = 0; c < 13; c++) { Xb[c] = Yb[c]; kb[c] = (h / 6.0) * Yb[c]; }
+#pragma unroll 1
+    for (int s = 3; s >= 0; s--) {
+        double sb[13];
+#pragma unroll
+        for (int c = 0; c < 13; c++) sb[c] = 0.0;
+        src.load(s, St, inv_s);
+        ode_bwd_nn<WPT, TERR>(mc, lane0, St, ul, ur, kb, sb, acc);
+        if (s > 0) {
+            renorm_bwd(St, inv_s, sb);  // stage input s = N(X + c_s k_s)
+            const double cs = (s == 3) ? h : .5 * h;
+            const double wk = (s == 1) ? (h / 6.0) : (h / 3.0);  // weight of k_s in the output combination
+#pragma unroll
+            for (int c = 0; c < 13; c++) { Xb[c] += sb[c]; kb[c] = fma(cs, sb[c], wk * Yb[c]); }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 13; c++) Xb[c] += sb[c];
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 13; c++) lam[c] = Xb[c];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Loss of one row (VehicleSystem::loss, src/VehicleSystem.cpp:70-92) and its gradient w.r.t. the
+// 13 live states:  l = |wrap(yaw - yaw_gt)| + sqrt((x_gt - x)^2 + (y_gt - y)^2)
+// ------------------------------------------------------------------------------------------------
+AVS_HD double row_loss(const double X[13], double yaw_gt, double x_gt, double y_gt, double scale, double lam[13]) {
+    const double qx = X[0], qy = X[1], qz = X[2], qw = X[3];
+    const double xe = x_gt - X[4], ye = y_gt - X[5];
+    const double lin = sqrt(xe * xe + ye * ye);
+    const double s = 2 * (qw * qz + qx * qy), c = 1 - 2 * (qy * qy + qz * qz);  // utils.cpp:75-77
+    const double yaw = atan2(s, c);
+    const double e = yaw - yaw_gt;
+    const double wr = atan2(sin(e), cos(e));
+    if (lam) {
+        if (lin > 0.0) {
+            lam[4] -= scale * xe / lin;
+            lam[5] -= scale * ye / lin;
+        }
+        const double sg = wr > 0.0 ? 1.0 : (wr < 0.0 ? -1.0 : 0.0);  // CppAD abs'(0) = 0
+        const double g = scale * sg / (s * s + c * c);
+        const double sb = g * c, cb = -g * s;
+        lam[0] += sb * 2 * qy;
+        lam[1] += sb * 2 * qx + cb * (-4 * qy);
+        lam[2] += sb * 2 * qw + cb * (-4 * qz);
+        lam[3] += sb * 2 * qz;
+    }
+    return fabs(wr) + lin;
+}
+
+// AI_b^-1: host-side precomputation (double; called once per context)
+inline void compute_AIinv(double out[6][6]) {
+    // I_b (generated/inertia_properties.cpp:8-12)
+    double AI[6][6] = {{0}};
+    AI[0][0] = kIbxx;  AI[0][1] = -kIbxy; AI[0][2] = -kIbxz;
+    AI[1][0] = -kIbxy; AI[1][1] = kIbyy;  AI[1][2] = -kIbyz;
+    AI[2][0] = -kIbxz; AI[2][1] = -kIbyz; AI[2][2] = kIbzz;
+    const double c[3] = {kCx, 0.0, kCz};
+    const double cx[3][3] = {{0, -c[2], c[1]}, {c[2], 0, -c[0]}, {-c[1], c[0], 0}};
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { AI[i][3 + j] = kMb * cx[i][j]; AI[3 + i][j] = -kMb * cx[i][j]; }
+    for (int i = 0; i < 3; i++) AI[3 + i][3 + i] = kMb;
+    // + sum_i X_i^T Ia X_i, Ia = diag-ish(Ixx, Iyy', 0 | m, m, m) in the wheel frame
+    for (int w = 0; w < 4; w++) {
+        double tx, ty;
+        wheel_sign(w, tx, ty);
+        double X[6][6] = {{0}};
+        X[0][0] = 1; X[1][2] = -1; X[2][1] = 1;
+        X[3][1] = kTz; X[3][2] = -ty; X[3][3] = 1;
+        X[4][0] = -ty; X[4][1] = tx;  X[4][5] = -1;
+        X[5][0] = -kTz; X[5][2] = tx; X[5][4] = 1;
+        const double Ia[6] = {kIwxx, kIwyyA, 0.0, kMw, kMw, kMw};
+        for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) {
+            double s = 0;
+            for (int k = 0; k < 6; k++) s += X[k][i] * Ia[k] * X[k][j];
+            AI[i][j] += s;
+        }
+    }
+    // Gauss-Jordan inverse with partial pivoting (6x6, SPD, cond ~ 50)
+    double M[6][12];
+    for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) { M[i][j] = AI[i][j]; M[i][6 + j] = (i == j) ? 1.0 : 0.0; }
+    for (int col = 0; col < 6; col++) {
+        int piv = col;
+        for (int r = col + 1; r < 6; r++) if (fabs(M[r][col]) > fabs(M[piv][col])) piv = r;
+        if (piv != col) for (int j = 0; j < 12; j++) { double t = M[col][j]; M[col][j] = M[piv][j]; M[piv][j] = t; }
+        const double d = 1.0 / M[col][col];
+        for (int j = 0; j < 12; j++) M[col][j] *= d;
+        for (int r = 0; r < 6; r++) if (r != col) {
+            const double f = M[r][col];
+            for (int j = 0; j < 12; j++) M[r][j] -= f * M[col][j];
+        }
+    }
+    // symmetrise
+    for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) out[i][j] = 0.5 * (M[i][6 + j] + M[j][6 + i]);
+}
+
+}  // namespace avs

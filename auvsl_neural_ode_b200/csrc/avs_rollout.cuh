@@ -1,0 +1,187 @@
+// avs_rollout.cuh — per-vehicle rollout drivers (forward sweep, reverse sweep) shared by the CUDA
+// kernels (avs_kernels.cu) and the CPU unit-test harness (tests/hostcheck).
+//
+// Replaces, per vehicle (paths relative to /root/reference):
+//   forward : Trainer::evaluateTrajectory / trainTrajectory rollout loops (src/Trainer.cpp:550-575,
+//             617-639) -> VehicleSystem::integrate (src/VehicleSystem.cpp:113-148) -> RK4
+//   reverse : the CppAD tape + ADFun::Reverse(1) of Trainer::trainTrajectory (src/Trainer.cpp:607-657)
+//
+// HBM data layout (all fp64, SoA so that lane-adjacent vehicles coalesce; n = vehicle index):
+//   x0      [21][N]          initial state, reference layout (HybridDynamics.h:65-69)
+//   ctrl    [T-1][2][N]      (vl, vr) applied during macro step i -> i+1 (= traj[i].vl/vr, Trainer.cpp:564-565)
+//   x_list  [T][23][N]       optional: the reference's x_list (row 0 = x0 + controls of row 0)
+//   x_final [21][N]          optional
+//   ckpt    [S*4][14][Nc] + [13][Nc]   stage inputs of every RK4 step (S = (T-1)*substeps), each with the
+//                            inverse quaternion norm that produced it, + the final state: what the reverse
+//                            sweep needs instead of a tape (448 B per vehicle-step)
+//   gt      [T][3][N]        (yaw, x, y) ground truth rows
+//   loss    [N], gps [104][N] per-sample loss and gradient w.r.t. the live tire-network weights
+#pragma once
+#include "avs_model.cuh"
+
+namespace avs {
+
+struct RolloutArgs {
+    int N;   // stride (total vehicles) of the caller-facing arrays; pointers are pre-offset to the chunk start
+    int Nc;  // vehicles handled by this launch (chunk) = stride of ckpt
+    int T, substeps;
+    const double* x0;
+    const double* ctrl;
+    double* x_list;
+    double* x_final;
+    double* ckpt;
+    const double* gt;
+    double* loss;
+    double* gps;
+};
+
+AVS_HD double ld(const double* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
+constexpr int kCkRows = 14;  // 13 live states + 1 inverse norm per stage record
+
+// writes stage records straight to HBM (only the writer lane of a group stores)
+struct CkptSink {
+    double* base;  // &ckpt[step][0][0][n]
+    size_t stride; // Nc
+    bool on;
+    AVS_HD void stage(int s, const double* T, double inv) {
+        if (!on) return;
+        double* p = base + (size_t)s * kCkRows * stride;
+#pragma unroll
+        for (int c = 0; c < 13; c++) p[(size_t)c * stride] = T[c];
+        if (s > 0) p[(size_t)13 * stride] = inv;
+    }
+    AVS_HD void finish(double inv) {
+        if (on) base[(size_t)13 * stride] = inv;  // stage 0 record carries the inverse norm of the step output
+    }
+};
+struct CkptSrc {
+    const double* base;
+    size_t stride;
+    AVS_HD void load(int s, double* St, double& inv) const {
+        const double* p = base + (size_t)s * kCkRows * stride;
+#pragma unroll
+        for (int c = 0; c < 13; c++) St[c] = ld(p + (size_t)c * stride);
+        inv = ld(p + (size_t)13 * stride);
+    }
+};
+
+// live-state index -> reference 21-state index
+AVS_HD constexpr int live_to_ref(int c) { return c < 7 ? c : c + 4; }
+
+template <int WPT, int TIRE, int TERR, bool STORE>
+AVS_HD void rollout_fwd_body(const ModelConst& mc, const RolloutArgs& a, int n, int lane0, bool valid) {
+    const size_t N = (size_t)a.N, NK = (size_t)a.Nc;
+    const bool writer = (lane0 == 0) && valid;
+    double X[13], jp[4];
+#pragma unroll
+    for (int c = 0; c < 13; c++) X[c] = ld(a.x0 + (size_t)live_to_ref(c) * N + n);
+#pragma unroll
+    for (int j = 0; j < 4; j++) jp[j] = ld(a.x0 + (size_t)(7 + j) * N + n);
+    if (a.x_list && writer) {
+        // row 0 = initial 23-vector: state as given + the controls of row 0 (Trainer.cpp:561-562, 610-611)
+        for (int c = 0; c < 21; c++) a.x_list[(size_t)c * N + n] = ld(a.x0 + (size_t)c * N + n);
+        a.x_list[(size_t)21 * N + n] = a.T > 1 ? ld(a.ctrl + n) : 0.0;
+        a.x_list[(size_t)22 * N + n] = a.T > 1 ? ld(a.ctrl + N + n) : 0.0;
+    }
+    double ul = 0.0, ur = 0.0;
+    for (int i = 1; i < a.T; i++) {
+        ul = ld(a.ctrl + ((size_t)(i - 1) * 2 + 0) * N + n);
+        ur = ld(a.ctrl + ((size_t)(i - 1) * 2 + 1) * N + n);
+        // joint positions: X[7..10] += (ts/6)(k1 + 2k2 + 2k3 + k4) with k = (vl,vr,vl,vr) (HybridDynamics.cpp:495, 615-618)
+        const double il = (kDt / 6.0) * (((ul + 2 * ul) + 2 * ul) + ul);
+        const double ir = (kDt / 6.0) * (((ur + 2 * ur) + 2 * ur) + ur);
+        for (int s = 0; s < a.substeps; s++) {
+            double Xn[13];
+            if (STORE) {
+                CkptSink sink{a.ckpt + ((size_t)((size_t)(i - 1) * a.substeps + s) * 4) * kCkRows * NK + n, NK, writer};
+                rk4_fwd<WPT, TIRE, TERR>(mc, lane0, X, ul, ur, Xn, sink);
+            } else {
+                NullSink sink;
+                rk4_fwd<WPT, TIRE, TERR>(mc, lane0, X, ul, ur, Xn, sink);
+            }
+#pragma unroll
+            for (int c = 0; c < 13; c++) X[c] = Xn[c];
+            jp[0] += il; jp[1] += ir; jp[2] += il; jp[3] += ir;
+        }
+        if (a.x_list && writer) {
+            double* row = a.x_list + (size_t)i * 23 * N + n;
+#pragma unroll
+            for (int c = 0; c < 13; c++) row[(size_t)live_to_ref(c) * N] = X[c];
+#pragma unroll
+            for (int j = 0; j < 4; j++) row[(size_t)(7 + j) * N] = jp[j];
+            row[(size_t)17 * N] = ul; row[(size_t)18 * N] = ur; row[(size_t)19 * N] = ul; row[(size_t)20 * N] = ur;
+            row[(size_t)21 * N] = 0.0; row[(size_t)22 * N] = 0.0;  // VehicleSystem.cpp:144-147
+        }
+    }
+    if (STORE && writer) {
+        double* base = a.ckpt + ((size_t)(a.T - 1) * a.substeps * 4) * kCkRows * NK + n;
+#pragma unroll
+        for (int c = 0; c < 13; c++) base[(size_t)c * NK] = X[c];
+    }
+    if (a.x_final && writer) {
+#pragma unroll
+        for (int c = 0; c < 13; c++) a.x_final[(size_t)live_to_ref(c) * N + n] = X[c];
+#pragma unroll
+        for (int j = 0; j < 4; j++) a.x_final[(size_t)(7 + j) * N + n] = jp[j];
+        // joint velocities hold the last applied control (or the caller's initial values when T == 1)
+        a.x_final[(size_t)17 * N + n] = a.T > 1 ? ul : ld(a.x0 + (size_t)17 * N + n);
+        a.x_final[(size_t)18 * N + n] = a.T > 1 ? ur : ld(a.x0 + (size_t)18 * N + n);
+        a.x_final[(size_t)19 * N + n] = a.T > 1 ? ul : ld(a.x0 + (size_t)19 * N + n);
+        a.x_final[(size_t)20 * N + n] = a.T > 1 ? ur : ld(a.x0 + (size_t)20 * N + n);
+    }
+}
+
+// Reverse sweep over the checkpoints written by rollout_fwd_body<.., STORE=true>.
+//   L = (sum_{i=1}^{T-1} l_i) / T / traj_len   (Trainer.cpp:612-649)
+template <int WPT, int TERR, class Acc>
+AVS_HD void rollout_bwd_body(const ModelConst& mc, const RolloutArgs& a, int n, int lane0, Acc& acc, double& loss_out) {
+    const size_t N = (size_t)a.N, NK = (size_t)a.Nc;
+    const int T = a.T;
+    // traj_len = sum |d(x,y)_gt| ; 0 -> 1   (Trainer.cpp:635-647)
+    double traj_len = 0.0;
+    {
+        double px = ld(a.gt + ((size_t)0 * 3 + 1) * N + n), py = ld(a.gt + ((size_t)0 * 3 + 2) * N + n);
+        for (int i = 1; i < T; i++) {
+            const double x = ld(a.gt + ((size_t)i * 3 + 1) * N + n), y = ld(a.gt + ((size_t)i * 3 + 2) * N + n);
+            const double dx = x - px, dy = y - py;
+            traj_len += sqrt(dx * dx + dy * dy);
+            px = x; py = y;
+        }
+    }
+    if (traj_len == 0.0) traj_len = 1.0;
+    const double seed = 1.0 / (double)T / traj_len;
+
+    double lam[13], Xn[13];
+#pragma unroll
+    for (int c = 0; c < 13; c++) lam[c] = 0.0;
+    {
+        const double* base = a.ckpt + ((size_t)(T - 1) * a.substeps * 4) * kCkRows * NK + n;
+#pragma unroll
+        for (int c = 0; c < 13; c++) Xn[c] = ld(base + (size_t)c * NK);
+    }
+    double lsum = 0.0;
+    for (int i = T - 1; i >= 1; i--) {
+        const double yaw_gt = ld(a.gt + ((size_t)i * 3 + 0) * N + n);
+        const double x_gt = ld(a.gt + ((size_t)i * 3 + 1) * N + n);
+        const double y_gt = ld(a.gt + ((size_t)i * 3 + 2) * N + n);
+        lsum += row_loss(Xn, yaw_gt, x_gt, y_gt, seed, lam);
+        const double ul = ld(a.ctrl + ((size_t)(i - 1) * 2 + 0) * N + n);
+        const double ur = ld(a.ctrl + ((size_t)(i - 1) * 2 + 1) * N + n);
+        for (int s = a.substeps - 1; s >= 0; s--) {
+            CkptSrc src{a.ckpt + ((size_t)((size_t)(i - 1) * a.substeps + s) * 4) * kCkRows * NK + n, NK};
+            rk4_bwd_nn<WPT, TERR>(mc, lane0, src, Xn, ul, ur, lam, acc);
+            double inv_unused;
+            src.load(0, Xn, inv_unused);  // this step's input is the previous step's output
+        }
+    }
+    loss_out = lsum * seed;
+}
+
+}  // namespace avs

@@ -1,0 +1,159 @@
+// CPU unit-test harness for the device math in auvsl_neural_ode_b200/csrc/avs_model.cuh and
+// avs_rollout.cuh: the same __host__ __device__ templates the sm_100a kernels are built from,
+// compiled by g++ with one thread owning all four wheels (WPT = 4).  Used only by tests/ (CPU
+// suite) to check the constant-folded ODE, the RK4 step and the hand-written adjoint against
+// oracle/ without a GPU.  Not part of the shipped library.
+#include <cstring>
+#include <vector>
+#include "../../auvsl_neural_ode_b200/csrc/avs_rollout.cuh"
+#include "../../auvsl_neural_ode_b200/csrc/avs_weights.h"
+
+using namespace avs;
+
+struct ArraySink {
+    double St[4][13], inv[4];
+    void stage(int s, const double* T, double i) { for (int c = 0; c < 13; c++) St[s][c] = T[c]; if (s > 0) inv[s] = i; }
+    void finish(double i) { inv[0] = i; }
+    void load(int s, double* out, double& i) const { for (int c = 0; c < 13; c++) out[c] = St[s][c]; i = inv[s]; }
+};
+
+struct HostAcc {
+    double g[kNumLive];
+    HostAcc() { for (int i = 0; i < kNumLive; i++) g[i] = 0; }
+    void add(int k, double v) { g[k] += v; }
+};
+
+static void fill_mc(ModelConst& mc, const double* p416, const double* zw152, const double* bek5, const double* height, const double* soil,
+                    int nx, int ny, double x0, double y0, double dx, double dy) {
+    memset(&mc, 0, sizeof(mc));
+    if (p416) {
+        memcpy(mc.W0, p416 + kOffW0, sizeof(mc.W0));
+        memcpy(mc.W2, p416 + kOffW2, sizeof(mc.W2));
+        memcpy(mc.W4, p416 + kOffW4, sizeof(mc.W4));
+    }
+    if (zw152) {
+        memcpy(mc.Z0, zw152, sizeof(mc.Z0));
+        memcpy(mc.Z2, zw152 + 8, sizeof(mc.Z2));
+        memcpy(mc.Z4, zw152 + 72, sizeof(mc.Z4));
+    }
+    if (bek5) memcpy(mc.bek, bek5, sizeof(mc.bek));
+    compute_AIinv(mc.AIinv);
+    mc.terr_kind = 0;
+    mc.grid.height = height; mc.grid.soil = soil; mc.grid.nx = nx; mc.grid.ny = ny;
+    mc.grid.x0 = x0; mc.grid.y0 = y0; mc.grid.inv_dx = 1.0 / dx; mc.grid.inv_dy = 1.0 / dy;
+}
+
+template <int TIRE, int TERR> static void ode13(const ModelConst& mc, const double* X13, const double* u, double* Xd13) {
+    ode_fwd<4, TIRE, TERR>(mc, 0, X13, u[0], u[1], Xd13);
+}
+template <int TIRE, int TERR> static void rk413(const ModelConst& mc, const double* X13, const double* u, double* Xn13, double* stages) {
+    ArraySink sink;
+    rk4_fwd<4, TIRE, TERR>(mc, 0, X13, u[0], u[1], Xn13, sink);
+    if (stages) memcpy(stages, sink.St, sizeof(sink.St));
+}
+
+#define DISPATCH(FN, tire, terr, ...)                                                          \
+    do {                                                                                       \
+        if (tire == 0) {                                                                       \
+            if (terr == 0) FN<0, 0>(__VA_ARGS__); else if (terr == 1) FN<0, 1>(__VA_ARGS__);   \
+            else if (terr == 2) FN<0, 2>(__VA_ARGS__); else FN<0, 3>(__VA_ARGS__);             \
+        } else {                                                                               \
+            if (terr == 0) FN<1, 0>(__VA_ARGS__); else if (terr == 1) FN<1, 1>(__VA_ARGS__);   \
+            else if (terr == 2) FN<1, 2>(__VA_ARGS__); else FN<1, 3>(__VA_ARGS__);             \
+        }                                                                                      \
+    } while (0)
+
+template <int TIRE, int TERR> static void fwd_body(const ModelConst& mc, const RolloutArgs& a, int n, bool store) {
+    if (store) rollout_fwd_body<4, TIRE, TERR, true>(mc, a, n, 0, true);
+    else rollout_fwd_body<4, TIRE, TERR, false>(mc, a, n, 0, true);
+}
+template <int TERR> static void bwd_body(const ModelConst& mc, const RolloutArgs& a, int n, HostAcc& acc, double& loss) {
+    rollout_bwd_body<4, TERR>(mc, a, n, 0, acc, loss);
+}
+
+extern "C" {
+
+struct hc_model {
+    int tire, terr, nx, ny;
+    double x0, y0, dx, dy;
+    const double* params;  // 416 (NN) or 5 (Bekker)
+    const double* zw;      // 152 fixed z-net weights (Z0[8], Z2[64], Z4[8]) — NN only
+    const double* height;
+    const double* soil;
+};
+
+static void mk(const hc_model* m, ModelConst& mc) {
+    fill_mc(mc, m->tire == 0 ? m->params : nullptr, m->zw, m->tire == 1 ? m->params : nullptr, m->height, m->soil, m->nx, m->ny, m->x0, m->y0,
+            m->dx > 0 ? m->dx : 1.0, m->dy > 0 ? m->dy : 1.0);
+}
+
+void hc_zweights(double* out152) { memcpy(out152, kFixedZ0, 64); memcpy(out152 + 8, kFixedZ2, 512); memcpy(out152 + 72, kFixedZ4, 64); }
+void hc_default_params(double* p416) { for (int k = 0; k < 4; k++) { memcpy(p416 + 104 * k, kDefaultW0, 192); memcpy(p416 + 104 * k + 24, kDefaultW2, 512); memcpy(p416 + 104 * k + 88, kDefaultW4, 128); } }
+void hc_aiinv(double* out36) { double A[6][6]; compute_AIinv(A); memcpy(out36, A, sizeof(A)); }
+double hc_tanh(double x) { return tanh_f64(x); }
+
+void hc_ode(const hc_model* m, const double* X13, const double* u2, double* Xd13) {
+    ModelConst mc; mk(m, mc);
+    DISPATCH(ode13, m->tire, m->terr, mc, X13, u2, Xd13);
+}
+void hc_rk4(const hc_model* m, const double* X13, const double* u2, double* Xn13, double* stages52) {
+    ModelConst mc; mk(m, mc);
+    DISPATCH(rk413, m->tire, m->terr, mc, X13, u2, Xn13, stages52);
+}
+// vector-Jacobian product of the ODE: Xb = (df/dX)^T Xdb, gW = (df/dW)^T Xdb
+void hc_ode_vjp(const hc_model* m, const double* X13, const double* u2, const double* Xdb13, double* Xb13, double* gW104) {
+    ModelConst mc; mk(m, mc);
+    HostAcc acc;
+    for (int c = 0; c < 13; c++) Xb13[c] = 0;
+    switch (m->terr) {
+        case 0: ode_bwd_nn<4, 0>(mc, 0, X13, u2[0], u2[1], Xdb13, Xb13, acc); break;
+        case 1: ode_bwd_nn<4, 1>(mc, 0, X13, u2[0], u2[1], Xdb13, Xb13, acc); break;
+        case 2: ode_bwd_nn<4, 2>(mc, 0, X13, u2[0], u2[1], Xdb13, Xb13, acc); break;
+        default: ode_bwd_nn<4, 3>(mc, 0, X13, u2[0], u2[1], Xdb13, Xb13, acc); break;
+    }
+    memcpy(gW104, acc.g, sizeof(acc.g));
+}
+// vector-Jacobian product of one RK4 step
+void hc_rk4_vjp(const hc_model* m, const double* X13, const double* u2, const double* lam_in13, double* lam_out13, double* gW104) {
+    ModelConst mc; mk(m, mc);
+    HostAcc acc;
+    double Xn[13], lam[13];
+    ArraySink sk;
+    memcpy(lam, lam_in13, sizeof(lam));
+    switch (m->terr) {
+        case 0: rk4_fwd<4, 0, 0>(mc, 0, X13, u2[0], u2[1], Xn, sk); rk4_bwd_nn<4, 0>(mc, 0, sk, Xn, u2[0], u2[1], lam, acc); break;
+        case 1: rk4_fwd<4, 0, 1>(mc, 0, X13, u2[0], u2[1], Xn, sk); rk4_bwd_nn<4, 1>(mc, 0, sk, Xn, u2[0], u2[1], lam, acc); break;
+        case 2: rk4_fwd<4, 0, 2>(mc, 0, X13, u2[0], u2[1], Xn, sk); rk4_bwd_nn<4, 2>(mc, 0, sk, Xn, u2[0], u2[1], lam, acc); break;
+        default: rk4_fwd<4, 0, 3>(mc, 0, X13, u2[0], u2[1], Xn, sk); rk4_bwd_nn<4, 3>(mc, 0, sk, Xn, u2[0], u2[1], lam, acc); break;
+    }
+    memcpy(lam_out13, lam, sizeof(lam));
+    memcpy(gW104, acc.g, sizeof(acc.g));
+}
+// SoA batch rollout, same buffers as the kernels
+void hc_rollout(const hc_model* m, int N, int T, int substeps, const double* x0, const double* ctrl, double* x_list, double* x_final) {
+    ModelConst mc; mk(m, mc);
+    RolloutArgs a; memset(&a, 0, sizeof(a));
+    a.N = N; a.Nc = N; a.T = T; a.substeps = substeps; a.x0 = x0; a.ctrl = ctrl; a.x_list = x_list; a.x_final = x_final;
+    for (int n = 0; n < N; n++) DISPATCH(fwd_body, m->tire, m->terr, mc, a, n, false);
+}
+void hc_rollout_grad(const hc_model* m, int N, int T, int substeps, const double* x0, const double* ctrl, const double* gt, double* loss, double* gps104xN) {
+    ModelConst mc; mk(m, mc);
+    std::vector<double> ckpt(((size_t)(T - 1) * substeps * 4 * kCkRows + 13) * N);
+    RolloutArgs a; memset(&a, 0, sizeof(a));
+    a.N = N; a.Nc = N; a.T = T; a.substeps = substeps; a.x0 = x0; a.ctrl = ctrl; a.ckpt = ckpt.data(); a.gt = gt;
+    for (int n = 0; n < N; n++) {
+        DISPATCH(fwd_body, 0, m->terr, mc, a, n, true);
+        HostAcc acc;
+        double L;
+        switch (m->terr) {
+            case 0: bwd_body<0>(mc, a, n, acc, L); break;
+            case 1: bwd_body<1>(mc, a, n, acc, L); break;
+            case 2: bwd_body<2>(mc, a, n, acc, L); break;
+            default: bwd_body<3>(mc, a, n, acc, L); break;
+        }
+        loss[n] = L;
+        for (int k = 0; k < kNumLive; k++) gps104xN[(size_t)k * N + n] = acc.g[k];
+    }
+}
+
+}  // extern "C"
