@@ -21,8 +21,8 @@ EXPORTS = [
     "avs_create", "avs_destroy", "avs_last_error", "avs_strerror", "avs_nn_default_params", "avs_bekker_default_params",
     "avs_set_nn_params", "avs_get_nn_params", "avs_set_bekker_params", "avs_get_bekker_params", "avs_set_terrain_analytic",
     "avs_set_terrain_grid", "avs_set_checkpoint_budget", "avs_whole_body_com", "avs_init_state_com", "avs_settle", "avs_ode",
-    "avs_rollout", "avs_rollout_dev", "avs_rollout_grad", "avs_rollout_grad_dev", "avs_rmsprop_step_dev", "avs_reset_optimizer",
-    "avs_stream", "avs_sync", "avs_kernel_launches", "avs_last_kernel_ms", "avs_measure_fp64_peak",
+    "avs_rollout", "avs_rollout_dev", "avs_rollout_grad", "avs_rollout_grad_dev", "avs_rmsprop_step_dev", "avs_rmsprop_step", "avs_reset_optimizer",
+    "avs_stream", "avs_set_stream", "avs_sync", "avs_kernel_launches", "avs_last_kernel_ms", "avs_measure_fp64_peak",
 ]
 
 
@@ -61,9 +61,11 @@ def lib():
         L.avs_rollout_grad.argtypes = [vp, i32, i32, i32, vp, vp, vp, dbl, i32, vp, vp, vp]
         L.avs_rollout_grad_dev.argtypes = [vp, i32, i32, i32, vp, vp, vp, dbl, i32, vp, vp, vp]
         L.avs_rmsprop_step_dev.argtypes = [vp, vp, dbl, dbl]
+        L.avs_rmsprop_step.argtypes = [vp, vp, dbl, dbl]
         L.avs_reset_optimizer.argtypes = [vp]
         L.avs_stream.argtypes = [vp]
         L.avs_stream.restype = vp
+        L.avs_set_stream.argtypes = [vp, vp]
         L.avs_sync.argtypes = [vp]
         L.avs_kernel_launches.argtypes = [vp]
         L.avs_kernel_launches.restype = C.c_longlong
@@ -219,12 +221,20 @@ class Context:
     def rmsprop_step_dev(self, d_reduced, lr=1e-3, l1_weight=0.0):
         self._ck(lib().avs_rmsprop_step_dev(self._h, d_reduced, float(lr), float(l1_weight)))
 
+    def rmsprop_step(self, reduced_host, lr=1e-3, l1_weight=0.0):
+        r = _f64(reduced_host)
+        assert r.size == REDUCED_LEN
+        self._ck(lib().avs_rmsprop_step(self._h, _p(r), float(lr), float(l1_weight)))
+
     def reset_optimizer(self):
         self._ck(lib().avs_reset_optimizer(self._h))
 
     @property
     def stream(self):
         return lib().avs_stream(self._h)
+
+    def set_stream(self, cuda_stream_handle):
+        self._ck(lib().avs_set_stream(self._h, cuda_stream_handle or None))
 
     def sync(self):
         self._ck(lib().avs_sync(self._h))

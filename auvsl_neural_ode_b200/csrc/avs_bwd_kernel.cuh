@@ -4,47 +4,46 @@
 // (/root/reference/src/Trainer.cpp:607-657).  Per RK4 step it reloads the four stage records the forward
 // sweep stored (coalesced, 448 B per vehicle-step), recomputes each stage's tire-network activations in
 // registers and immediately back-propagates through them.  dL/dW is accumulated per lane in a private
-// shared-memory column ([104][kBwdBlock] doubles, conflict-free: consecutive lanes -> consecutive banks),
-// summed over the lanes of a vehicle at the end and written as the per-sample gradient gps[104][N].
+// shared-memory column ([104][kBwdBlock] doubles next to 65 scratch rows for the loop-carried adjoints,
+// conflict-free: consecutive lanes -> consecutive banks), summed over the lanes of a vehicle at the end and
+// written as the per-sample gradient gps[104][N].
 #pragma once
-#include "avs_kernels.h"
+#include "avs_dev.cuh"
 
 namespace avs {
 
-struct SmemAcc {
-    double* col;  // &smem[threadIdx.x]; element k lives at col[k * kBwdBlock]
-    __device__ __forceinline__ void add(int k, double v) { col[k * kBwdBlock] += v; }
-};
+constexpr int kBwdSlotG = kBwdScratch;  // gradient accumulators follow the scratch columns
 
 template <int TERR>
-__global__ void __launch_bounds__(kBwdBlock) rollout_bwd_kernel(const __grid_constant__ ModelConst mc, const __grid_constant__ RolloutArgs a) {
-    extern __shared__ double smem[];
-        const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(kBwdBlock) rollout_bwd_kernel(const __grid_constant__ RolloutArgs a) {
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     int n = gid >> 2;
     const int lane0 = gid & 3;
     const bool valid = n < a.Nc;
     if (!valid) n = a.Nc - 1;
-    SmemAcc acc{smem + threadIdx.x};
+    const Scratch<kBwdBlock> G = scratch_col<kBwdBlock>(kBwdSlotG);
 #pragma unroll 8
-    for (int k = 0; k < kNumLive; k++) acc.col[k * kBwdBlock] = 0.0;
+    for (int k = 0; k < kNumLive; k++) G[k] = 0.0;
     double loss;
-    rollout_bwd_body<1, TERR>(mc, a, n, lane0, acc, loss);
+    auto mk_odeb = [lane0](double ul, double ur) { return OdeBwdCall<TERR, kBwdBlock>{lane0, 39, 26, 52, kBwdSlotG, ul, ur}; };
+    rollout_bwd_body(a, n, loss, scratch_col<kBwdBlock>(0), mk_odeb);
     const bool writer = valid && lane0 == 0;
     for (int k = 0; k < kNumLive; k++) {
-        const double g = Group<1>::sum(acc.col[k * kBwdBlock]);
+        const double g = Group<1>::sum(G[k]);
         if (writer) a.gps[(size_t)k * a.N + n] = g;
     }
     if (writer) a.loss[n] = loss;
 }
 
-
 template <int TERR> static cudaError_t launch_bwd_t(const ModelConst& mc, const RolloutArgs& a, cudaStream_t s) {
     const long long threads = (long long)a.Nc * 4;
     const int grid = (int)((threads + kBwdBlock - 1) / kBwdBlock);
-    const size_t smem = (size_t)kNumLive * kBwdBlock * sizeof(double);
+    const size_t smem = (size_t)(kNumLive + kBwdScratch) * kBwdBlock * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(rollout_bwd_kernel<TERR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    rollout_bwd_kernel<TERR><<<grid, kBwdBlock, smem, s>>>(mc, a);
+    e = upload_model(mc, s);
+    if (e != cudaSuccess) return e;
+    rollout_bwd_kernel<TERR><<<grid, kBwdBlock, smem, s>>>(a);
     return cudaGetLastError();
 }
 

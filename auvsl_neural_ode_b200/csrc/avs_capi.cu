@@ -32,6 +32,7 @@ struct avs_ctx {
     int terr = AVS_TERRAIN_FLAT;
     unsigned long long ckpt_budget = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool ev_fwd = false, ev_bwd = false;
     ModelConst mc;
@@ -129,7 +130,8 @@ int avs_create(avs_ctx** out, int device, int tire_model) {
     memcpy(ctx->mc.bek, kBekkerDefault, sizeof(kBekkerDefault));
     compute_AIinv(ctx->mc.AIinv);
     ctx->mc.grid.inv_dx = ctx->mc.grid.inv_dy = 1.0;
-    bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+    bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
+    ctx->stream = ctx->own_stream;
     for (int i = 0; i < 4 && ok; i++) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_params, sizeof(double) * AVS_NUM_NN_PARAMS) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_sq, sizeof(double) * AVS_NUM_NN_PARAMS) == cudaSuccess;
@@ -148,7 +150,7 @@ void avs_destroy(avs_ctx* ctx) {
     if (ctx->d_params) cudaFree(ctx->d_params);
     if (ctx->d_sq) cudaFree(ctx->d_sq);
     for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
 
@@ -395,7 +397,22 @@ int avs_rmsprop_step_dev(avs_ctx* ctx, const double* d_reduced, double lr, doubl
     return AVS_OK;
 }
 
+int avs_rmsprop_step(avs_ctx* ctx, const double* reduced_host, double lr, double l1_weight) {
+    if (!ctx || !reduced_host) return fail(ctx, AVS_E_ARG, "avs_rmsprop_step: null argument");
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->reduced.reserve(AVS_REDUCED_LEN * 8));
+    CK(cudaMemcpyAsync(ctx->reduced.p, reduced_host, AVS_REDUCED_LEN * 8, cudaMemcpyHostToDevice, ctx->stream));
+    return avs_rmsprop_step_dev(ctx, ctx->reduced.as<double>(), lr, l1_weight);
+}
+
 void* avs_stream(avs_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int avs_set_stream(avs_ctx* ctx, void* stream) {
+    if (!ctx) return AVS_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = stream ? (cudaStream_t)stream : ctx->own_stream;
+    return AVS_OK;
+}
 int avs_sync(avs_ctx* ctx) {
     if (!ctx) return AVS_E_ARG;
     CK(cudaSetDevice(ctx->device));

@@ -1,0 +1,72 @@
+// avs_dev.cuh — device-only glue shared by the rollout kernels: the per-TU __constant__ copy of the model,
+// the dynamic shared-memory scratch and the NON-inlined ODE / ODE-adjoint entry points.
+//
+// Why non-inlined: ptxas schedules the body of a rolled loop for minimum register pressure and turns the
+// eight interleaved tanh/matvec dependency chains back into serial chains (measured: 30-40 % of all FP64
+// instructions issue back-to-back on the result of their predecessor, vs 1-5 % for the same code compiled as a
+// stand-alone function).  With one warp per SM sub-partition (N = 4096 vehicles x 4 lanes = 512 warps on 592
+// sub-partitions) instruction-level parallelism is the only latency hiding there is.
+// Why __constant__ and not a kernel parameter: a non-inlined callee would have to reach a by-reference kernel
+// parameter through generic loads; a module-scope __constant__ object keeps every weight a constant-bank
+// operand (c[0x3][imm]) of the DFMA that uses it.
+#pragma once
+#include "avs_kernels.h"
+
+namespace avs {
+
+extern __shared__ double g_smem[];
+static __constant__ ModelConst c_mc;
+
+template <int BLOCK> __device__ __forceinline__ Scratch<BLOCK> scratch_col(int slot) {
+    return Scratch<BLOCK>{g_smem + slot * BLOCK + threadIdx.x};
+}
+
+// K = f(T):  T, K = scratch slots (13 columns each)
+template <int TIRE, int TERR, int BLOCK>
+__device__ __noinline__ void ode_fwd_call(int lane0, int slotT, int slotK, double ul, double ur) {
+    const Scratch<BLOCK> T = scratch_col<BLOCK>(slotT), K = scratch_col<BLOCK>(slotK);
+    double X[13], Xd[13];
+#pragma unroll
+    for (int c = 0; c < 13; c++) X[c] = T[c];
+    ode_fwd<1, TIRE, TERR>(c_mc, lane0, X, ul, ur, Xd);
+#pragma unroll
+    for (int c = 0; c < 13; c++) K[c] = Xd[c];
+}
+template <int TIRE, int TERR, int BLOCK> struct OdeFwdCall {
+    int lane0, slotT, slotK;
+    double ul, ur;
+    __device__ __forceinline__ void operator()(Scratch<BLOCK>, Scratch<BLOCK>) const { ode_fwd_call<TIRE, TERR, BLOCK>(lane0, slotT, slotK, ul, ur); }
+};
+
+// gradient accumulators: slot `slotG` + k, one private shared-memory column per lane
+template <int BLOCK> struct SmemAcc {
+    double* col;
+    __device__ __forceinline__ void fma(int k, double a, double b) { col[k * BLOCK] = ::fma(a, b, col[k * BLOCK]); }
+};
+
+// SB = (df/dX)^T KB at XS, dL/dW += ...
+template <int TERR, int BLOCK>
+__device__ __noinline__ void ode_bwd_call(int lane0, int slotXS, int slotKB, int slotSB, int slotG, double ul, double ur) {
+    const Scratch<BLOCK> XS = scratch_col<BLOCK>(slotXS), KB = scratch_col<BLOCK>(slotKB), SB = scratch_col<BLOCK>(slotSB);
+    SmemAcc<BLOCK> acc{g_smem + slotG * BLOCK + threadIdx.x};
+    double X[13], Xb[13];
+#pragma unroll
+    for (int c = 0; c < 13; c++) X[c] = XS[c];
+    ode_bwd_nn<1, TERR>(c_mc, lane0, X, ul, ur, KB, Xb, acc);
+#pragma unroll
+    for (int c = 0; c < 13; c++) SB[c] = Xb[c];
+}
+template <int TERR, int BLOCK> struct OdeBwdCall {
+    int lane0, slotXS, slotKB, slotSB, slotG;
+    double ul, ur;
+    __device__ __forceinline__ void operator()(Scratch<BLOCK>, Scratch<BLOCK>, Scratch<BLOCK>) const {
+        ode_bwd_call<TERR, BLOCK>(lane0, slotXS, slotKB, slotSB, slotG, ul, ur);
+    }
+};
+
+// upload the model into this TU's __constant__ copy (stream-ordered, before the launch that reads it)
+static inline cudaError_t upload_model(const ModelConst& mc, cudaStream_t s) {
+    return cudaMemcpyToSymbolAsync(c_mc, &mc, sizeof(ModelConst), 0, cudaMemcpyHostToDevice, s);
+}
+
+}  // namespace avs

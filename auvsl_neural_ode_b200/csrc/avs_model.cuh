@@ -145,6 +145,77 @@ AVS_HD double tanh_f64(double x) {
     return copysign(t, x);
 }
 
+// W-wide tanh, in place.  Same arithmetic as tanh_f64, but every step is issued for all W elements
+// before the next step starts: with one warp per SM sub-partition the only latency hiding available is
+// instruction-level parallelism, and ptxas does not interleave separately inlined dependent chains.
+template <int W> AVS_HD void tanh_vec(double* x) {
+    const double L2E = 1.4426950408889634e+0, MAGIC = 6755399441055744.0;
+    const double LN2_HI = 6.93147180559945286e-01, LN2_LO = 2.31904681384629956e-17;
+    double a[W], t[W], r[W], p[W];
+#pragma unroll
+    for (int i = 0; i < W; i++) a[i] = -2.0 * fabs(x[i]);
+#pragma unroll
+    for (int i = 0; i < W; i++) t[i] = fma(a[i], L2E, MAGIC);
+#pragma unroll
+    for (int i = 0; i < W; i++) r[i] = t[i] - MAGIC;
+#pragma unroll
+    for (int i = 0; i < W; i++) a[i] = fma(r[i], -LN2_HI, a[i]);
+#pragma unroll
+    for (int i = 0; i < W; i++) r[i] = fma(r[i], -LN2_LO, a[i]);
+#pragma unroll
+    for (int i = 0; i < W; i++) p[i] = fma(2.5110049204818658e-08, r[i], 2.763265472252779e-07);
+#define AVS_POLY_STEP(C)           \
+    _Pragma("unroll") for (int i = 0; i < W; i++) p[i] = fma(p[i], r[i], C);
+    AVS_POLY_STEP(2.755724088722987e-06)
+    AVS_POLY_STEP(2.4801485441561313e-05)
+    AVS_POLY_STEP(0.00019841269890076403)
+    AVS_POLY_STEP(0.0013888888952352863)
+    AVS_POLY_STEP(0.008333333333319589)
+    AVS_POLY_STEP(0.04166666666648795)
+    AVS_POLY_STEP(0.1666666666666668)
+    AVS_POLY_STEP(0.5000000000000019)
+    AVS_POLY_STEP(1.0)
+    AVS_POLY_STEP(1.0)
+#undef AVS_POLY_STEP
+    // e = p * 2^k
+#pragma unroll
+    for (int i = 0; i < W; i++) {
+#if defined(__CUDA_ARCH__)
+        int k = __double2loint(t[i]);
+        k = max(k, -1000);
+        p[i] = __hiloint2double(__double2hiint(p[i]) + (k << 20), __double2loint(p[i]));
+#else
+        int64_t k = (int64_t)(t[i] - MAGIC);
+        if (k < -1000) k = -1000;
+        p[i] = ldexp(p[i], (int)k);
+#endif
+    }
+    // (1 - e) / (1 + e)
+#pragma unroll
+    for (int i = 0; i < W; i++) { a[i] = 1.0 + p[i]; p[i] = 1.0 - p[i]; }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+    for (int i = 0; i < W; i++) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r[i]) : "d"(a[i]));
+#pragma unroll
+    for (int i = 0; i < W; i++) t[i] = fma(-a[i], r[i], 1.0);
+#pragma unroll
+    for (int i = 0; i < W; i++) t[i] = fma(t[i], t[i], t[i]);
+#pragma unroll
+    for (int i = 0; i < W; i++) r[i] = fma(r[i], t[i], r[i]);
+#pragma unroll
+    for (int i = 0; i < W; i++) t[i] = p[i] * r[i];
+#pragma unroll
+    for (int i = 0; i < W; i++) p[i] = fma(-a[i], t[i], p[i]);
+#pragma unroll
+    for (int i = 0; i < W; i++) t[i] = fma(p[i], r[i], t[i]);
+#else
+#pragma unroll
+    for (int i = 0; i < W; i++) t[i] = p[i] / a[i];
+#endif
+#pragma unroll
+    for (int i = 0; i < W; i++) x[i] = copysign(t[i], x[i]);
+}
+
 AVS_HD double rsqrt_f64(double x) {  // for quaternion re-normalisation, x ~ 1
 #if defined(__CUDA_ARCH__)
     return rsqrt(x);
@@ -167,6 +238,16 @@ template <int WPT> struct Group {
 #endif
         return x;
     }
+};
+
+// Per-thread scratch column: element c lives at p[c * STRIDE].  On the device p points into shared memory
+// at &buf[threadIdx.x] with STRIDE = blockDim.x (consecutive lanes -> consecutive banks, conflict-free);
+// on the host STRIDE = 1 over a local array.  Loop-carried rollout state lives here so that the registers
+// are free for the instruction-level parallelism of the ODE evaluation.
+template <int STRIDE> struct Scratch {
+    double* p;
+    AVS_HD double& operator[](int c) const { return p[c * STRIDE]; }
+    AVS_HD Scratch sub(int c0) const { return Scratch{p + c0 * STRIDE}; }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -235,35 +316,48 @@ struct NNAct {
     double z4;
 };
 
-// in: contact velocity (vx, vy), wheel speed w, sinkage zr -> (Fx, Fy, Fz) before the damping term
+// in: contact velocity (vx, vy), wheel speed w, sinkage zr -> (Fx, Fy, Fz) before the damping term.
+// Loop nests are ordered so that consecutive instructions belong to different accumulators (ILP).
 AVS_HD void tire_nn_fwd(const ModelConst& mc, double vx, double vy, double w, double zr, double F[3], NNAct& a) {
     const double s0 = zr * (1.0 / kInStd0);
     a.s1 = (w * kTireRadius - vx) * (1.0 / kInStd1);
     a.s2 = w * (1.0 / kInStd2);
     a.s3 = vy * (1.0 / kInStd3);
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-        a.h0[j] = tanh_f64(fma(mc.W0[j][2], a.s3, fma(mc.W0[j][1], a.s2, mc.W0[j][0] * a.s1)));
-        a.g0[j] = tanh_f64(mc.Z0[j] * s0);
+    for (int j = 0; j < 8; j++) { a.h0[j] = mc.W0[j][0] * a.s1; a.g0[j] = mc.Z0[j] * s0; }
+#pragma unroll
+    for (int j = 0; j < 8; j++) a.h0[j] = fma(mc.W0[j][1], a.s2, a.h0[j]);
+#pragma unroll
+    for (int j = 0; j < 8; j++) a.h0[j] = fma(mc.W0[j][2], a.s3, a.h0[j]);
+    tanh_vec<8>(a.h0);
+    tanh_vec<8>(a.g0);
+#pragma unroll
+    for (int j = 0; j < 8; j++) { a.h2[j] = mc.W2[j][0] * a.h0[0]; a.g2[j] = mc.Z2[j][0] * a.g0[0]; }
+#pragma unroll
+    for (int k = 1; k < 8; k++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) { a.h2[j] = fma(mc.W2[j][k], a.h0[k], a.h2[j]); a.g2[j] = fma(mc.Z2[j][k], a.g0[k], a.g2[j]); }
     }
+    tanh_vec<8>(a.h2);
+    tanh_vec<8>(a.g2);
+    // three output rows, each as two interleaved partial sums
+    double f0a = mc.W4[0][0] * a.h2[0], f0b = mc.W4[0][1] * a.h2[1];
+    double f1a = mc.W4[1][0] * a.h2[0], f1b = mc.W4[1][1] * a.h2[1];
+    double z4a = mc.Z4[0] * a.g2[0], z4b = mc.Z4[1] * a.g2[1];
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-        double sx = mc.W2[j][0] * a.h0[0], sz = mc.Z2[j][0] * a.g0[0];
-#pragma unroll
-        for (int k = 1; k < 8; k++) { sx = fma(mc.W2[j][k], a.h0[k], sx); sz = fma(mc.Z2[j][k], a.g0[k], sz); }
-        a.h2[j] = tanh_f64(sx);
-        a.g2[j] = tanh_f64(sz);
+    for (int k = 2; k < 8; k += 2) {
+        f0a = fma(mc.W4[0][k], a.h2[k], f0a); f0b = fma(mc.W4[0][k + 1], a.h2[k + 1], f0b);
+        f1a = fma(mc.W4[1][k], a.h2[k], f1a); f1b = fma(mc.W4[1][k + 1], a.h2[k + 1], f1b);
+        z4a = fma(mc.Z4[k], a.g2[k], z4a);    z4b = fma(mc.Z4[k + 1], a.g2[k + 1], z4b);
     }
-    double f0 = mc.W4[0][0] * a.h2[0], f1 = mc.W4[1][0] * a.h2[0], z4 = mc.Z4[0] * a.g2[0];
-#pragma unroll
-    for (int k = 1; k < 8; k++) { f0 = fma(mc.W4[0][k], a.h2[k], f0); f1 = fma(mc.W4[1][k], a.h2[k], f1); z4 = fma(mc.Z4[k], a.g2[k], z4); }
+    const double z4 = z4a + z4b;
     a.z4 = z4;
-    F[0] = f0 * kOutStd0;
-    F[1] = f1 * kOutStd1;
+    F[0] = (f0a + f0b) * kOutStd0;
+    F[1] = (f1a + f1b) * kOutStd1;
     F[2] = (z4 > 0.0 ? z4 : 0.0) * kOutStd2;  // relu = CondExpGt(x,0,x,0) (TireNetwork.cpp:47-50)
 }
 
-// adjoint: Fbar[3] -> (vx_bar, vy_bar, zr_bar) and dL/dW accumulation through acc.add(k, value)
+// adjoint: Fbar[3] -> (vx_bar, vy_bar, zr_bar) and dL/dW accumulation through acc.fma(k, a, b): g[k] += a*b
 template <class Acc>
 AVS_HD void tire_nn_bwd(const ModelConst& mc, const NNAct& a, const double Fbar[3], double& vxb, double& vyb, double& zrb, Acc& acc) {
     const double o0 = Fbar[0] * kOutStd0, o1 = Fbar[1] * kOutStd1;
@@ -271,40 +365,47 @@ AVS_HD void tire_nn_bwd(const ModelConst& mc, const NNAct& a, const double Fbar[
     double d2[8], e2[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-        acc.add(kOffW4 + k, o0 * a.h2[k]);
-        acc.add(kOffW4 + 8 + k, o1 * a.h2[k]);
-        const double hb = fma(mc.W4[1][k], o1, mc.W4[0][k] * o0);
-        d2[k] = hb * fma(-a.h2[k], a.h2[k], 1.0);
-        e2[k] = (mc.Z4[k] * oz) * fma(-a.g2[k], a.g2[k], 1.0);
+        acc.fma(kOffW4 + k, o0, a.h2[k]);
+        acc.fma(kOffW4 + 8 + k, o1, a.h2[k]);
     }
+#pragma unroll
+    for (int k = 0; k < 8; k++) { d2[k] = fma(mc.W4[1][k], o1, mc.W4[0][k] * o0); e2[k] = mc.Z4[k] * oz; }
+#pragma unroll
+    for (int k = 0; k < 8; k++) { d2[k] *= fma(-a.h2[k], a.h2[k], 1.0); e2[k] *= fma(-a.g2[k], a.g2[k], 1.0); }
     double d0[8], e0[8];
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        double hb = mc.W2[0][k] * d2[0], gb = mc.Z2[0][k] * e2[0];
+    for (int k = 0; k < 8; k++) { d0[k] = mc.W2[0][k] * d2[0]; e0[k] = mc.Z2[0][k] * e2[0]; }
 #pragma unroll
-        for (int j = 1; j < 8; j++) { hb = fma(mc.W2[j][k], d2[j], hb); gb = fma(mc.Z2[j][k], e2[j], gb); }
-        d0[k] = hb * fma(-a.h0[k], a.h0[k], 1.0);
-        e0[k] = gb * fma(-a.g0[k], a.g0[k], 1.0);
+    for (int j = 1; j < 8; j++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) { d0[k] = fma(mc.W2[j][k], d2[j], d0[k]); e0[k] = fma(mc.Z2[j][k], e2[j], e0[k]); }
     }
+#pragma unroll
+    for (int k = 0; k < 8; k++) { d0[k] *= fma(-a.h0[k], a.h0[k], 1.0); e0[k] *= fma(-a.g0[k], a.g0[k], 1.0); }
 #pragma unroll
     for (int j = 0; j < 8; j++) {
 #pragma unroll
-        for (int k = 0; k < 8; k++) acc.add(kOffW2 + j * 8 + k, d2[j] * a.h0[k]);
+        for (int k = 0; k < 8; k++) acc.fma(kOffW2 + j * 8 + k, d2[j], a.h0[k]);
     }
-    double s1b = 0.0, s2b = 0.0, s3b = 0.0, s0b = 0.0;
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-        acc.add(kOffW0 + j * 3 + 0, d0[j] * a.s1);
-        acc.add(kOffW0 + j * 3 + 1, d0[j] * a.s2);
-        acc.add(kOffW0 + j * 3 + 2, d0[j] * a.s3);
-        s1b = fma(mc.W0[j][0], d0[j], s1b);
-        s3b = fma(mc.W0[j][2], d0[j], s3b);
-        s0b = fma(mc.Z0[j], e0[j], s0b);
+        acc.fma(kOffW0 + j * 3 + 0, d0[j], a.s1);
+        acc.fma(kOffW0 + j * 3 + 1, d0[j], a.s2);
+        acc.fma(kOffW0 + j * 3 + 2, d0[j], a.s3);
     }
-    (void)s2b;  // wheel speed is a control, not differentiated
-    vxb = -s1b * (1.0 / kInStd1);
-    vyb = s3b * (1.0 / kInStd3);
-    zrb = s0b * (1.0 / kInStd0);
+    double s1a = mc.W0[0][0] * d0[0], s1b = mc.W0[1][0] * d0[1];
+    double s3a = mc.W0[0][2] * d0[0], s3b = mc.W0[1][2] * d0[1];
+    double s0a = mc.Z0[0] * e0[0], s0b = mc.Z0[1] * e0[1];
+#pragma unroll
+    for (int j = 2; j < 8; j += 2) {
+        s1a = fma(mc.W0[j][0], d0[j], s1a); s1b = fma(mc.W0[j + 1][0], d0[j + 1], s1b);
+        s3a = fma(mc.W0[j][2], d0[j], s3a); s3b = fma(mc.W0[j + 1][2], d0[j + 1], s3b);
+        s0a = fma(mc.Z0[j], e0[j], s0a);    s0b = fma(mc.Z0[j + 1], e0[j + 1], s0b);
+    }
+    // wheel speed (s2) is a control, not differentiated
+    vxb = -(s1a + s1b) * (1.0 / kInStd1);
+    vyb = (s3a + s3b) * (1.0 / kInStd3);
+    zrb = (s0a + s0b) * (1.0 / kInStd0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -338,7 +439,7 @@ struct WheelAct {
     double n0, n1, n2;        // I_w * omega_w
 };
 
-struct NullAcc { AVS_HD void add(int, double) {} };
+struct NullAcc { AVS_HD void fma(int, double, double) {} };
 
 // wheel index i: 0 FL(+,+) 1 FR(+,-) 2 RL(-,+) 3 RR(-,-); qd = commanded wheel speed
 template <int TERR>
@@ -484,32 +585,38 @@ AVS_HD void base_fwd(const ModelConst& mc, const double R[9], const double X[13]
     Xd[12] += kGravity * R[8];
 }
 
-// adjoint of base_fwd: Xdb[13] -> Sb[6] (= adjoint of every wheel contribution), += Xb[13], += Rb[9]
-AVS_HD void base_bwd(const ModelConst& mc, const double R[9], const double X[13], const double Xdb[13], double Sb[6], double Xb[13], double Rb[9]) {
+// adjoint of base_fwd, part 1: Sb[6] = -AIinv^T Xdb[7..12] = adjoint of every wheel contribution.
+// XD is anything indexable (array or scratch column).
+template <class XD> AVS_HD void base_bwd_S(const ModelConst& mc, const XD& Xdb, double Sb[6]) {
+    const double l0 = Xdb[7];
+#pragma unroll
+    for (int c = 0; c < 6; c++) Sb[c] = mc.AIinv[0][c] * l0;
+#pragma unroll
+    for (int r = 1; r < 6; r++) {
+        const double l = Xdb[7 + r];
+#pragma unroll
+        for (int c = 0; c < 6; c++) Sb[c] = fma(mc.AIinv[r][c], l, Sb[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < 6; c++) Sb[c] = -Sb[c];
+}
+
+// adjoint of base_fwd, part 2: everything that flows into X and R.  Xb[13] and Rb[9] are OVERWRITTEN.
+template <class XD>
+AVS_HD void base_bwd_rest(const double R[9], const double X[13], const XD& Xdb, const double Sb[6], double Xb[13], double Rb[9]) {
     const double* q = X; const double* w = X + 7; const double* v = X + 10;
     double* qb = Xb; double* wb = Xb + 7; double* vb = Xb + 10;
-    // acceleration rows
-#pragma unroll
-    for (int c = 0; c < 6; c++) {
-        double s = mc.AIinv[0][c] * Xdb[7];
-#pragma unroll
-        for (int r = 1; r < 6; r++) s = fma(mc.AIinv[r][c], Xdb[7 + r], s);
-        Sb[c] = -s;
-    }
-    Rb[6] += kGravity * Xdb[10];
-    Rb[7] += kGravity * Xdb[11];
-    Rb[8] += kGravity * Xdb[12];
     double nB[3], fB[3];
     base_inertia_mul(w, v, nB, fB);
     const double* a = Sb; const double* b = Sb + 3;
     // pb_n = w x nB + v x fB ; pb_f = w x fB
     double nBb[3], fBb[3];
-    wb[0] += (nB[1] * a[2] - nB[2] * a[1]) + (fB[1] * b[2] - fB[2] * b[1]);
-    wb[1] += (nB[2] * a[0] - nB[0] * a[2]) + (fB[2] * b[0] - fB[0] * b[2]);
-    wb[2] += (nB[0] * a[1] - nB[1] * a[0]) + (fB[0] * b[1] - fB[1] * b[0]);
-    vb[0] += fB[1] * a[2] - fB[2] * a[1];
-    vb[1] += fB[2] * a[0] - fB[0] * a[2];
-    vb[2] += fB[0] * a[1] - fB[1] * a[0];
+    wb[0] = (nB[1] * a[2] - nB[2] * a[1]) + (fB[1] * b[2] - fB[2] * b[1]);
+    wb[1] = (nB[2] * a[0] - nB[0] * a[2]) + (fB[2] * b[0] - fB[0] * b[2]);
+    wb[2] = (nB[0] * a[1] - nB[1] * a[0]) + (fB[0] * b[1] - fB[1] * b[0]);
+    vb[0] = fB[1] * a[2] - fB[2] * a[1];
+    vb[1] = fB[2] * a[0] - fB[0] * a[2];
+    vb[2] = fB[0] * a[1] - fB[1] * a[0];
     nBb[0] = a[1] * w[2] - a[2] * w[1];
     nBb[1] = a[2] * w[0] - a[0] * w[2];
     nBb[2] = a[0] * w[1] - a[1] * w[0];
@@ -533,17 +640,19 @@ AVS_HD void base_bwd(const ModelConst& mc, const double R[9], const double X[13]
     wb[0] += q[3] * l0 + q[2] * l1 - q[1] * l2 - q[0] * l3;
     wb[1] += -q[2] * l0 + q[3] * l1 + q[0] * l2 - q[1] * l3;
     wb[2] += q[1] * l0 - q[0] * l1 + q[3] * l2 - q[2] * l3;
-    qb[0] += -w[2] * l1 + w[1] * l2 - w[0] * l3;
-    qb[1] += w[2] * l0 - w[0] * l2 - w[1] * l3;
-    qb[2] += -w[1] * l0 + w[0] * l1 - w[2] * l3;
-    qb[3] += w[0] * l0 + w[1] * l1 + w[2] * l2;
-    // pdot = R v
-    vb[0] += R[0] * Xdb[4] + R[3] * Xdb[5] + R[6] * Xdb[6];
-    vb[1] += R[1] * Xdb[4] + R[4] * Xdb[5] + R[7] * Xdb[6];
-    vb[2] += R[2] * Xdb[4] + R[5] * Xdb[5] + R[8] * Xdb[6];
-    Rb[0] += Xdb[4] * v[0]; Rb[1] += Xdb[4] * v[1]; Rb[2] += Xdb[4] * v[2];
-    Rb[3] += Xdb[5] * v[0]; Rb[4] += Xdb[5] * v[1]; Rb[5] += Xdb[5] * v[2];
-    Rb[6] += Xdb[6] * v[0]; Rb[7] += Xdb[6] * v[1]; Rb[8] += Xdb[6] * v[2];
+    qb[0] = -w[2] * l1 + w[1] * l2 - w[0] * l3;
+    qb[1] = w[2] * l0 - w[0] * l2 - w[1] * l3;
+    qb[2] = -w[1] * l0 + w[0] * l1 - w[2] * l3;
+    qb[3] = w[0] * l0 + w[1] * l1 + w[2] * l2;
+    // pdot = R v ; g_b = R^T (0,0,g)
+    const double p0 = Xdb[4], p1 = Xdb[5], p2 = Xdb[6];
+    vb[0] += R[0] * p0 + R[3] * p1 + R[6] * p2;
+    vb[1] += R[1] * p0 + R[4] * p1 + R[7] * p2;
+    vb[2] += R[2] * p0 + R[5] * p1 + R[8] * p2;
+    Rb[0] = p0 * v[0]; Rb[1] = p0 * v[1]; Rb[2] = p0 * v[2];
+    Rb[3] = p1 * v[0]; Rb[4] = p1 * v[1]; Rb[5] = p1 * v[2];
+    Rb[6] = fma(p2, v[0], kGravity * Xdb[10]); Rb[7] = fma(p2, v[1], kGravity * Xdb[11]); Rb[8] = fma(p2, v[2], kGravity * Xdb[12]);
+    Xb[4] = 0.0; Xb[5] = 0.0; Xb[6] = 0.0;
 }
 
 }  // namespace avs
@@ -591,14 +700,16 @@ AVS_HD void ode_fwd(const ModelConst& mc, int lane0, const double X[13], double 
     base_fwd(mc, R, X, S, Xd);
 }
 
-// Adjoint of the ODE at stage input X:  Xb += (df/dX)^T Xdb ; weight gradients into acc.
-// The wheel forward is recomputed here so that its activations never leave registers.
-template <int WPT, int TERR, class Acc>
-AVS_HD void ode_bwd_nn(const ModelConst& mc, int lane0, const double X[13], double ul, double ur, const double Xdb[13], double Xb[13], Acc& acc) {
+// Adjoint of the ODE at stage input X:  Xb = (df/dX)^T Xdb (overwritten) ; weight gradients into acc.
+// Xdb is indexable (scratch column).  The wheel forward is recomputed here so that its activations never
+// leave registers; the base-link part that needs X and R again runs after the wheel part so that nothing
+// but Sb[6] has to stay live across the tire network.
+template <int WPT, int TERR, class XD, class Acc>
+AVS_HD void ode_bwd_nn(const ModelConst& mc, int lane0, const double X[13], double ul, double ur, const XD& Xdb, double Xb[13], Acc& acc) {
     double R[9];
     quat_to_R(X, R);
-    double Sb[6], Rb[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    base_bwd(mc, R, X, Xdb, Sb, Xb, Rb);
+    double Sb[6];
+    base_bwd_S(mc, Xdb, Sb);
     // wheel-local adjoints, summed over the group: cp_bar (x) r  ->  Rb, pb ; wb ; vb
     double gx[3] = {0, 0, 0}, gy[3] = {0, 0, 0}, gs[3] = {0, 0, 0};  // sum sx*cpb, sum sy*cpb, sum cpb
     double wb[3] = {0, 0, 0}, vb[3] = {0, 0, 0};
@@ -635,6 +746,8 @@ AVS_HD void ode_bwd_nn(const ModelConst& mc, int lane0, const double X[13], doub
         gx[c] = Group<WPT>::sum(gx[c]); gy[c] = Group<WPT>::sum(gy[c]); gs[c] = Group<WPT>::sum(gs[c]);
         wb[c] = Group<WPT>::sum(wb[c]); vb[c] = Group<WPT>::sum(vb[c]);
     }
+    double Rb[9];
+    base_bwd_rest(R, X, Xdb, Sb, Xb, Rb);
     // cp = R r + p with r = (sx*kTx, sy*kTy, kRz)
 #pragma unroll
     for (int c = 0; c < 3; c++) {
@@ -651,82 +764,109 @@ AVS_HD void ode_bwd_nn(const ModelConst& mc, int lane0, const double X[13], doub
 // ------------------------------------------------------------------------------------------------
 // RK4 step with per-stage quaternion re-normalisation (HybridDynamics::RK4, HybridDynamics.cpp:461-502)
 // ------------------------------------------------------------------------------------------------
-AVS_HD void renorm(double Y[13], double& inv_norm) {
-    inv_norm = rsqrt_f64(Y[0] * Y[0] + Y[1] * Y[1] + Y[2] * Y[2] + Y[3] * Y[3]);
-    Y[0] *= inv_norm; Y[1] *= inv_norm; Y[2] *= inv_norm; Y[3] *= inv_norm;
+template <class V> AVS_HD void renorm(V&& Y, double& inv_norm) {
+    const double q0 = Y[0], q1 = Y[1], q2 = Y[2], q3 = Y[3];
+    inv_norm = rsqrt_f64(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
+    Y[0] = q0 * inv_norm; Y[1] = q1 * inv_norm; Y[2] = q2 * inv_norm; Y[3] = q3 * inv_norm;
 }
 // X = Y/|Y| on the quaternion part: Yb = (Xb - X (X.Xb)) / |Y|, in place
-AVS_HD void renorm_bwd(const double Xn[13], double inv_norm, double Xb[13]) {
-    const double d = Xn[0] * Xb[0] + Xn[1] * Xb[1] + Xn[2] * Xb[2] + Xn[3] * Xb[3];
-#pragma unroll
-    for (int c = 0; c < 4; c++) Xb[c] = (Xb[c] - Xn[c] * d) * inv_norm;
+template <class VX, class VB> AVS_HD void renorm_bwd(const VX& Xn, double inv_norm, VB&& Xb) {
+    const double x0 = Xn[0], x1 = Xn[1], x2 = Xn[2], x3 = Xn[3];
+    const double b0 = Xb[0], b1 = Xb[1], b2 = Xb[2], b3 = Xb[3];
+    const double d = x0 * b0 + x1 * b1 + x2 * b2 + x3 * b3;
+    Xb[0] = (b0 - x0 * d) * inv_norm; Xb[1] = (b1 - x1 * d) * inv_norm;
+    Xb[2] = (b2 - x2 * d) * inv_norm; Xb[3] = (b3 - x3 * d) * inv_norm;
 }
 
 // Stage sink: receives every (normalised) stage input and the inverse norm that produced it
 // (stage 0: the inverse norm of the step OUTPUT, delivered by finish()).  NullSink for plain rollouts.
 struct NullSink {
-    AVS_HD void stage(int, const double*, double) {}
+    template <class V> AVS_HD void stage(int, const V&, double) {}
     AVS_HD void finish(double) {}
 };
 
-// The four stages run as a rolled loop (one copy of the ODE in the instruction stream, registers sized
-// for a single evaluation); the stage weights of HybridDynamics.cpp:470-495 are selected by index.
-template <int WPT, int TIRE, int TERR, class Sink>
-AVS_HD void rk4_fwd(const ModelConst& mc, int lane0, const double X[13], double ul, double ur, double Xn[13], Sink& sink) {
-    double k[13], acc[13], T[13], inv = 1.0;
+// One RK4 step.  All loop-carried state lives in per-thread scratch columns (X in/out; ACC, T, K scratch,
+// 13 slots each); `ode(T, K)` evaluates K = f(T).  On the device `ode` is a call to a NON-inlined function:
+// ptxas schedules the body of a rolled loop for minimum register pressure and re-serialises independent
+// dependency chains, whereas a stand-alone function body keeps the interleaved (ILP) order it is written in.
+// The four stages run as a rolled loop; the stage weights of HybridDynamics.cpp:470-495 are selected by index.
+template <class Ode, class Sink, class St>
+AVS_HD void rk4_fwd(Ode& ode, St X, St ACC, St T, St K, Sink& sink) {
+    double inv = 1.0;
     const double h = kDt;
 #pragma unroll
-    for (int c = 0; c < 13; c++) { acc[c] = 0.0; T[c] = X[c]; }
+    for (int c = 0; c < 13; c++) { ACC[c] = 0.0; T[c] = X[c]; }
 #pragma unroll 1
     for (int s = 0; s < 4; s++) {
         sink.stage(s, T, inv);
-        ode_fwd<WPT, TIRE, TERR>(mc, lane0, T, ul, ur, k);
+        ode(T, K);
         const double wgt = (s == 0 || s == 3) ? 1.0 : 2.0;   // k1 + 2 k2 + 2 k3 + k4
         const double cs = (s == 2) ? h : .5 * h;             // X + .5h k1, X + .5h k2, X + h k3
 #pragma unroll
-        for (int c = 0; c < 13; c++) { acc[c] = fma(wgt, k[c], acc[c]); T[c] = fma(cs, k[c], X[c]); }
+        for (int c = 0; c < 13; c++) { const double k = K[c]; ACC[c] = fma(wgt, k, ACC[c]); T[c] = fma(cs, k, X[c]); }
         renorm(T, inv);
     }
 #pragma unroll
-    for (int c = 0; c < 13; c++) Xn[c] = fma(h / 6.0, acc[c], X[c]);
-    renorm(Xn, inv);
+    for (int c = 0; c < 13; c++) T[c] = fma(h / 6.0, ACC[c], X[c]);
+    renorm(T, inv);
+#pragma unroll
+    for (int c = 0; c < 13; c++) X[c] = T[c];
     sink.finish(inv);
 }
 
-// Adjoint of one RK4 step.  src.load(s, St, inv) returns stage input s and the inverse norm stored with it
-// (for s = 0: the inverse norm of the step output); Xn = the step's (normalised) output;
-// lam (in/out) = adjoint of Xn on entry, adjoint of the step input on return.
-template <int WPT, int TERR, class Src, class Acc>
-AVS_HD void rk4_bwd_nn(const ModelConst& mc, int lane0, Src& src, const double Xn[13], double ul, double ur, double lam[13], Acc& acc) {
+// Adjoint of one RK4 step.  src.load(s, XS, inv) fills the scratch column XS with stage input s and returns
+// the inverse norm stored with it (s = 0: the inverse norm of the step output, also via load_inv);
+// Xnq = quaternion of the step's (normalised) output.  `odeb(XS, KB, SB)` computes SB = (df/dX)^T KB at
+// stage input XS (and accumulates the weight gradient).  LAM (13, in/out) = adjoint of the step output on
+// entry, adjoint of the step input on return; YB, KB, XS, SB are scratch columns.
+template <class OdeB, class Src, class St>
+AVS_HD void rk4_bwd_nn(OdeB& odeb, Src& src, const double Xnq[4], St LAM, St YB, St KB, St XS, St SB) {
     const double h = kDt;
-    double Yb[13], Xb[13], kb[13], St[13], inv_s;
-    src.load(0, St, inv_s);  // only inv_s (norm of the step output) is needed before the stage loop
+    double inv_s;
+    src.load_inv(0, inv_s);
+    renorm_bwd(Xnq, inv_s, LAM);  // adjoint of Y+ = X + h/6 (k1 + 2k2 + 2k3 + k4) through the final normalisation
 #pragma unroll
-    for (int c = 0; c < 13; c++) Yb[c] = lam[c];
-    renorm_bwd(Xn, inv_s, Yb);  // adjoint of Y+ = X + h/6 (k1 + 2k2 + 2k3 + k4)
-#pragma unroll
-    for (int c = 0; c < 13; c++) { Xb[c] = Yb[c]; kb[c] = (h / 6.0) * Yb[c]; }
+    for (int c = 0; c < 13; c++) { const double l = LAM[c]; YB[c] = l; KB[c] = (h / 6.0) * l; }
 #pragma unroll 1
     for (int s = 3; s >= 0; s--) {
-        double sb[13];
-#pragma unroll
-        for (int c = 0; c < 13; c++) sb[c] = 0.0;
-        src.load(s, St, inv_s);
-        ode_bwd_nn<WPT, TERR>(mc, lane0, St, ul, ur, kb, sb, acc);
+        src.load(s, XS, inv_s);
+        odeb(XS, KB, SB);
         if (s > 0) {
-            renorm_bwd(St, inv_s, sb);  // stage input s = N(X + c_s k_s)
+            renorm_bwd(XS, inv_s, SB);  // stage input s = N(X + c_s k_s)
             const double cs = (s == 3) ? h : .5 * h;
             const double wk = (s == 1) ? (h / 6.0) : (h / 3.0);  // weight of k_s in the output combination
 #pragma unroll
-            for (int c = 0; c < 13; c++) { Xb[c] += sb[c]; kb[c] = fma(cs, sb[c], wk * Yb[c]); }
+            for (int c = 0; c < 13; c++) { const double b = SB[c]; LAM[c] += b; KB[c] = fma(cs, b, wk * YB[c]); }
         } else {
 #pragma unroll
-            for (int c = 0; c < 13; c++) Xb[c] += sb[c];
+            for (int c = 0; c < 13; c++) LAM[c] += SB[c];
         }
     }
-#pragma unroll
-    for (int c = 0; c < 13; c++) lam[c] = Xb[c];
 }
+
+// inline ODE functors (host harness; the device kernels use non-inlined calls, see avs_dev.cuh)
+template <int WPT, int TIRE, int TERR> struct OdeFwdInline {
+    const ModelConst& mc; int lane0; double ul, ur;
+    template <class St> AVS_HD void operator()(St T, St K) const {
+        double X[13], Xd[13];
+#pragma unroll
+        for (int c = 0; c < 13; c++) X[c] = T[c];
+        ode_fwd<WPT, TIRE, TERR>(mc, lane0, X, ul, ur, Xd);
+#pragma unroll
+        for (int c = 0; c < 13; c++) K[c] = Xd[c];
+    }
+};
+template <int WPT, int TERR, class Acc> struct OdeBwdInline {
+    const ModelConst& mc; int lane0; double ul, ur; Acc& acc;
+    template <class St> AVS_HD void operator()(St XS, St KB, St SB) const {
+        double X[13], Xb[13];
+#pragma unroll
+        for (int c = 0; c < 13; c++) X[c] = XS[c];
+        ode_bwd_nn<WPT, TERR>(mc, lane0, X, ul, ur, KB, Xb, acc);
+#pragma unroll
+        for (int c = 0; c < 13; c++) SB[c] = Xb[c];
+    }
+};
 
 // ------------------------------------------------------------------------------------------------
 // Loss of one row (VehicleSystem::loss, src/VehicleSystem.cpp:70-92) and its gradient w.r.t. the

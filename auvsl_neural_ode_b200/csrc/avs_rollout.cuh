@@ -50,7 +50,7 @@ struct CkptSink {
     double* base;  // &ckpt[step][0][0][n]
     size_t stride; // Nc
     bool on;
-    AVS_HD void stage(int s, const double* T, double inv) {
+    template <class V> AVS_HD void stage(int s, const V& T, double inv) {
         if (!on) return;
         double* p = base + (size_t)s * kCkRows * stride;
 #pragma unroll
@@ -64,26 +64,30 @@ struct CkptSink {
 struct CkptSrc {
     const double* base;
     size_t stride;
-    AVS_HD void load(int s, double* St, double& inv) const {
+    template <class V> AVS_HD void load(int s, V&& St, double& inv) const {
         const double* p = base + (size_t)s * kCkRows * stride;
 #pragma unroll
         for (int c = 0; c < 13; c++) St[c] = ld(p + (size_t)c * stride);
         inv = ld(p + (size_t)13 * stride);
     }
+    AVS_HD void load_inv(int s, double& inv) const { inv = ld(base + ((size_t)s * kCkRows + 13) * stride); }
 };
 
 // live-state index -> reference 21-state index
 AVS_HD constexpr int live_to_ref(int c) { return c < 7 ? c : c + 4; }
 
-template <int WPT, int TIRE, int TERR, bool STORE>
-AVS_HD void rollout_fwd_body(const ModelConst& mc, const RolloutArgs& a, int n, int lane0, bool valid) {
+constexpr int kFwdScratch = 56;  // X[13] | ACC[13] | T[13] | K[13] | joint positions[4]
+
+// S = per-thread scratch column with kFwdScratch slots; mk_ode(ul, ur) returns the functor K = f(T)
+template <bool STORE, class MkOde, class St>
+AVS_HD void rollout_fwd_body(const RolloutArgs& a, int n, int lane0, bool valid, St S, MkOde mk_ode) {
     const size_t N = (size_t)a.N, NK = (size_t)a.Nc;
     const bool writer = (lane0 == 0) && valid;
-    double X[13], jp[4];
+    St X = S, ACC = S.sub(13), TT = S.sub(26), KK = S.sub(39), JP = S.sub(52);
 #pragma unroll
     for (int c = 0; c < 13; c++) X[c] = ld(a.x0 + (size_t)live_to_ref(c) * N + n);
 #pragma unroll
-    for (int j = 0; j < 4; j++) jp[j] = ld(a.x0 + (size_t)(7 + j) * N + n);
+    for (int j = 0; j < 4; j++) JP[j] = ld(a.x0 + (size_t)(7 + j) * N + n);
     if (a.x_list && writer) {
         // row 0 = initial 23-vector: state as given + the controls of row 0 (Trainer.cpp:561-562, 610-611)
         for (int c = 0; c < 21; c++) a.x_list[(size_t)c * N + n] = ld(a.x0 + (size_t)c * N + n);
@@ -94,28 +98,27 @@ AVS_HD void rollout_fwd_body(const ModelConst& mc, const RolloutArgs& a, int n, 
     for (int i = 1; i < a.T; i++) {
         ul = ld(a.ctrl + ((size_t)(i - 1) * 2 + 0) * N + n);
         ur = ld(a.ctrl + ((size_t)(i - 1) * 2 + 1) * N + n);
-        // joint positions: X[7..10] += (ts/6)(k1 + 2k2 + 2k3 + k4) with k = (vl,vr,vl,vr) (HybridDynamics.cpp:495, 615-618)
-        const double il = (kDt / 6.0) * (((ul + 2 * ul) + 2 * ul) + ul);
-        const double ir = (kDt / 6.0) * (((ur + 2 * ur) + 2 * ur) + ur);
+        auto ode = mk_ode(ul, ur);
+#pragma unroll 1
         for (int s = 0; s < a.substeps; s++) {
-            double Xn[13];
             if (STORE) {
                 CkptSink sink{a.ckpt + ((size_t)((size_t)(i - 1) * a.substeps + s) * 4) * kCkRows * NK + n, NK, writer};
-                rk4_fwd<WPT, TIRE, TERR>(mc, lane0, X, ul, ur, Xn, sink);
+                rk4_fwd(ode, X, ACC, TT, KK, sink);
             } else {
                 NullSink sink;
-                rk4_fwd<WPT, TIRE, TERR>(mc, lane0, X, ul, ur, Xn, sink);
+                rk4_fwd(ode, X, ACC, TT, KK, sink);
             }
-#pragma unroll
-            for (int c = 0; c < 13; c++) X[c] = Xn[c];
-            jp[0] += il; jp[1] += ir; jp[2] += il; jp[3] += ir;
         }
+        // joint positions: X[7..10] += (ts/6)(k1 + 2k2 + 2k3 + k4) per RK4 step, k = (vl,vr,vl,vr) (HybridDynamics.cpp:495, 615-618)
+        const double il = (kDt / 6.0) * (((ul + 2 * ul) + 2 * ul) + ul);
+        const double ir = (kDt / 6.0) * (((ur + 2 * ur) + 2 * ur) + ur);
+        for (int s = 0; s < a.substeps; s++) { JP[0] += il; JP[1] += ir; JP[2] += il; JP[3] += ir; }
         if (a.x_list && writer) {
             double* row = a.x_list + (size_t)i * 23 * N + n;
 #pragma unroll
             for (int c = 0; c < 13; c++) row[(size_t)live_to_ref(c) * N] = X[c];
 #pragma unroll
-            for (int j = 0; j < 4; j++) row[(size_t)(7 + j) * N] = jp[j];
+            for (int j = 0; j < 4; j++) row[(size_t)(7 + j) * N] = JP[j];
             row[(size_t)17 * N] = ul; row[(size_t)18 * N] = ur; row[(size_t)19 * N] = ul; row[(size_t)20 * N] = ur;
             row[(size_t)21 * N] = 0.0; row[(size_t)22 * N] = 0.0;  // VehicleSystem.cpp:144-147
         }
@@ -129,7 +132,7 @@ AVS_HD void rollout_fwd_body(const ModelConst& mc, const RolloutArgs& a, int n, 
 #pragma unroll
         for (int c = 0; c < 13; c++) a.x_final[(size_t)live_to_ref(c) * N + n] = X[c];
 #pragma unroll
-        for (int j = 0; j < 4; j++) a.x_final[(size_t)(7 + j) * N + n] = jp[j];
+        for (int j = 0; j < 4; j++) a.x_final[(size_t)(7 + j) * N + n] = JP[j];
         // joint velocities hold the last applied control (or the caller's initial values when T == 1)
         a.x_final[(size_t)17 * N + n] = a.T > 1 ? ul : ld(a.x0 + (size_t)17 * N + n);
         a.x_final[(size_t)18 * N + n] = a.T > 1 ? ur : ld(a.x0 + (size_t)18 * N + n);
@@ -138,12 +141,16 @@ AVS_HD void rollout_fwd_body(const ModelConst& mc, const RolloutArgs& a, int n, 
     }
 }
 
+constexpr int kBwdScratch = 65;  // LAM[13] | YB[13] | KB[13] | XS[13] | SB[13]
+
 // Reverse sweep over the checkpoints written by rollout_fwd_body<.., STORE=true>.
 //   L = (sum_{i=1}^{T-1} l_i) / T / traj_len   (Trainer.cpp:612-649)
-template <int WPT, int TERR, class Acc>
-AVS_HD void rollout_bwd_body(const ModelConst& mc, const RolloutArgs& a, int n, int lane0, Acc& acc, double& loss_out) {
+// mk_odeb(ul, ur) returns the functor SB = (df/dX)^T KB at XS (accumulating dL/dW)
+template <class MkOdeB, class St>
+AVS_HD void rollout_bwd_body(const RolloutArgs& a, int n, double& loss_out, St S, MkOdeB mk_odeb) {
     const size_t N = (size_t)a.N, NK = (size_t)a.Nc;
     const int T = a.T;
+    St LAM = S, YB = S.sub(13), KB = S.sub(26), XS = S.sub(39), SB = S.sub(52);
     // traj_len = sum |d(x,y)_gt| ; 0 -> 1   (Trainer.cpp:635-647)
     double traj_len = 0.0;
     {
@@ -157,28 +164,35 @@ AVS_HD void rollout_bwd_body(const ModelConst& mc, const RolloutArgs& a, int n, 
     }
     if (traj_len == 0.0) traj_len = 1.0;
     const double seed = 1.0 / (double)T / traj_len;
-
-    double lam[13], Xn[13];
 #pragma unroll
-    for (int c = 0; c < 13; c++) lam[c] = 0.0;
-    {
-        const double* base = a.ckpt + ((size_t)(T - 1) * a.substeps * 4) * kCkRows * NK + n;
-#pragma unroll
-        for (int c = 0; c < 13; c++) Xn[c] = ld(base + (size_t)c * NK);
-    }
+    for (int c = 0; c < 13; c++) LAM[c] = 0.0;
+    // record holding the state AFTER the step being reversed: the next step's stage-0 record, or the final state
+    const double* next = a.ckpt + ((size_t)(T - 1) * a.substeps * 4) * kCkRows * NK + n;
     double lsum = 0.0;
     for (int i = T - 1; i >= 1; i--) {
-        const double yaw_gt = ld(a.gt + ((size_t)i * 3 + 0) * N + n);
-        const double x_gt = ld(a.gt + ((size_t)i * 3 + 1) * N + n);
-        const double y_gt = ld(a.gt + ((size_t)i * 3 + 2) * N + n);
-        lsum += row_loss(Xn, yaw_gt, x_gt, y_gt, seed, lam);
+        {
+            double Xr[13], lam[13];
+#pragma unroll
+            for (int c = 0; c < 13; c++) { Xr[c] = ld(next + (size_t)c * NK); lam[c] = 0.0; }
+            const double yaw_gt = ld(a.gt + ((size_t)i * 3 + 0) * N + n);
+            const double x_gt = ld(a.gt + ((size_t)i * 3 + 1) * N + n);
+            const double y_gt = ld(a.gt + ((size_t)i * 3 + 2) * N + n);
+            lsum += row_loss(Xr, yaw_gt, x_gt, y_gt, seed, lam);
+#pragma unroll
+            for (int c = 0; c < 6; c++) LAM[c] += lam[c];  // the row loss touches q and (x, y) only
+        }
         const double ul = ld(a.ctrl + ((size_t)(i - 1) * 2 + 0) * N + n);
         const double ur = ld(a.ctrl + ((size_t)(i - 1) * 2 + 1) * N + n);
+        auto odeb = mk_odeb(ul, ur);
+#pragma unroll 1
         for (int s = a.substeps - 1; s >= 0; s--) {
-            CkptSrc src{a.ckpt + ((size_t)((size_t)(i - 1) * a.substeps + s) * 4) * kCkRows * NK + n, NK};
-            rk4_bwd_nn<WPT, TERR>(mc, lane0, src, Xn, ul, ur, lam, acc);
-            double inv_unused;
-            src.load(0, Xn, inv_unused);  // this step's input is the previous step's output
+            const double* rec = a.ckpt + ((size_t)((size_t)(i - 1) * a.substeps + s) * 4) * kCkRows * NK + n;
+            CkptSrc src{rec, NK};
+            double Xnq[4];
+#pragma unroll
+            for (int c = 0; c < 4; c++) Xnq[c] = ld(next + (size_t)c * NK);
+            rk4_bwd_nn(odeb, src, Xnq, LAM, YB, KB, XS, SB);
+            next = rec;
         }
     }
     loss_out = lsum * seed;

@@ -121,10 +121,14 @@ int avs_rollout_grad_dev(avs_ctx* ctx, int N, int T, int substeps, const double*
  *      float-truncated gradient g = reduced[0..415] / reduced[417].  d_reduced is a DEVICE pointer
  *      (typically the all-reduced buffer); squared-gradient state lives in the context (starts at 1). */
 int avs_rmsprop_step_dev(avs_ctx* ctx, const double* d_reduced, double lr, double l1_weight);
+/* host variant: uploads reduced[418] first (e.g. after a host-side reduction over ranks) */
+int avs_rmsprop_step(avs_ctx* ctx, const double* reduced_host, double lr, double l1_weight);
 int avs_reset_optimizer(avs_ctx* ctx);
 
 /* ---- stream / bookkeeping */
 void* avs_stream(avs_ctx* ctx);                 /* cudaStream_t the *_dev calls are enqueued on */
+/* enqueue on a caller-owned cudaStream_t instead (NULL = back to the context's own stream) */
+int avs_set_stream(avs_ctx* ctx, void* stream);
 int avs_sync(avs_ctx* ctx);
 long long avs_kernel_launches(const avs_ctx* ctx); /* kernels launched by this context so far */
 /* average duration in ms of the most recent rollout kernels (CUDA events on the ctx stream; valid after avs_sync) */

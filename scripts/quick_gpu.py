@@ -18,7 +18,7 @@ for T, grad in ((Tf, False), (Tb, True)):
     dloss = torch.zeros(N, dtype=torch.float64, device=dev)
     dred = torch.zeros(418, dtype=torch.float64, device=dev)
     torch.cuda.synchronize()
-    for it in range(3):
+    for it in range(int(sys.argv[4]) if len(sys.argv) > 4 else 3):
         t0 = time.time()
         if grad:
             ctx.rollout_grad_dev(N, T, 10, dx0.data_ptr(), dctrl.data_ptr(), dgt.data_ptr(), dloss.data_ptr(), dred.data_ptr())

@@ -12,15 +12,16 @@ using namespace avs;
 
 struct ArraySink {
     double St[4][13], inv[4];
-    void stage(int s, const double* T, double i) { for (int c = 0; c < 13; c++) St[s][c] = T[c]; if (s > 0) inv[s] = i; }
+    template <class V> void stage(int s, const V& T, double i) { for (int c = 0; c < 13; c++) St[s][c] = T[c]; if (s > 0) inv[s] = i; }
     void finish(double i) { inv[0] = i; }
-    void load(int s, double* out, double& i) const { for (int c = 0; c < 13; c++) out[c] = St[s][c]; i = inv[s]; }
+    template <class V> void load(int s, V&& out, double& i) const { for (int c = 0; c < 13; c++) out[c] = St[s][c]; i = inv[s]; }
+    void load_inv(int s, double& i) const { i = inv[s]; }
 };
 
 struct HostAcc {
     double g[kNumLive];
     HostAcc() { for (int i = 0; i < kNumLive; i++) g[i] = 0; }
-    void add(int k, double v) { g[k] += v; }
+    void fma(int k, double a, double b) { g[k] += a * b; }
 };
 
 static void fill_mc(ModelConst& mc, const double* p416, const double* zw152, const double* bek5, const double* height, const double* soil,
@@ -48,7 +49,12 @@ template <int TIRE, int TERR> static void ode13(const ModelConst& mc, const doub
 }
 template <int TIRE, int TERR> static void rk413(const ModelConst& mc, const double* X13, const double* u, double* Xn13, double* stages) {
     ArraySink sink;
-    rk4_fwd<4, TIRE, TERR>(mc, 0, X13, u[0], u[1], Xn13, sink);
+    double sc[52];
+    Scratch<1> X{sc}, ACC{sc + 13}, TT{sc + 26}, KK{sc + 39};
+    for (int c = 0; c < 13; c++) X[c] = X13[c];
+    OdeFwdInline<4, TIRE, TERR> ode{mc, 0, u[0], u[1]};
+    rk4_fwd(ode, X, ACC, TT, KK, sink);
+    for (int c = 0; c < 13; c++) Xn13[c] = X[c];
     if (stages) memcpy(stages, sink.St, sizeof(sink.St));
 }
 
@@ -64,11 +70,15 @@ template <int TIRE, int TERR> static void rk413(const ModelConst& mc, const doub
     } while (0)
 
 template <int TIRE, int TERR> static void fwd_body(const ModelConst& mc, const RolloutArgs& a, int n, bool store) {
-    if (store) rollout_fwd_body<4, TIRE, TERR, true>(mc, a, n, 0, true);
-    else rollout_fwd_body<4, TIRE, TERR, false>(mc, a, n, 0, true);
+    double sc[kFwdScratch];
+    auto mk = [&mc](double ul, double ur) { return OdeFwdInline<4, TIRE, TERR>{mc, 0, ul, ur}; };
+    if (store) rollout_fwd_body<true>(a, n, 0, true, Scratch<1>{sc}, mk);
+    else rollout_fwd_body<false>(a, n, 0, true, Scratch<1>{sc}, mk);
 }
 template <int TERR> static void bwd_body(const ModelConst& mc, const RolloutArgs& a, int n, HostAcc& acc, double& loss) {
-    rollout_bwd_body<4, TERR>(mc, a, n, 0, acc, loss);
+    double sc[kBwdScratch];
+    auto mk = [&mc, &acc](double ul, double ur) { return OdeBwdInline<4, TERR, HostAcc>{mc, 0, ul, ur, acc}; };
+    rollout_bwd_body(a, n, loss, Scratch<1>{sc}, mk);
 }
 
 extern "C" {
@@ -104,12 +114,14 @@ void hc_rk4(const hc_model* m, const double* X13, const double* u2, double* Xn13
 void hc_ode_vjp(const hc_model* m, const double* X13, const double* u2, const double* Xdb13, double* Xb13, double* gW104) {
     ModelConst mc; mk(m, mc);
     HostAcc acc;
-    for (int c = 0; c < 13; c++) Xb13[c] = 0;
+    double kb[13];
+    memcpy(kb, Xdb13, sizeof(kb));
+    Scratch<1> KB{kb};
     switch (m->terr) {
-        case 0: ode_bwd_nn<4, 0>(mc, 0, X13, u2[0], u2[1], Xdb13, Xb13, acc); break;
-        case 1: ode_bwd_nn<4, 1>(mc, 0, X13, u2[0], u2[1], Xdb13, Xb13, acc); break;
-        case 2: ode_bwd_nn<4, 2>(mc, 0, X13, u2[0], u2[1], Xdb13, Xb13, acc); break;
-        default: ode_bwd_nn<4, 3>(mc, 0, X13, u2[0], u2[1], Xdb13, Xb13, acc); break;
+        case 0: ode_bwd_nn<4, 0>(mc, 0, X13, u2[0], u2[1], KB, Xb13, acc); break;
+        case 1: ode_bwd_nn<4, 1>(mc, 0, X13, u2[0], u2[1], KB, Xb13, acc); break;
+        case 2: ode_bwd_nn<4, 2>(mc, 0, X13, u2[0], u2[1], KB, Xb13, acc); break;
+        default: ode_bwd_nn<4, 3>(mc, 0, X13, u2[0], u2[1], KB, Xb13, acc); break;
     }
     memcpy(gW104, acc.g, sizeof(acc.g));
 }
@@ -117,15 +129,26 @@ void hc_ode_vjp(const hc_model* m, const double* X13, const double* u2, const do
 void hc_rk4_vjp(const hc_model* m, const double* X13, const double* u2, const double* lam_in13, double* lam_out13, double* gW104) {
     ModelConst mc; mk(m, mc);
     HostAcc acc;
-    double Xn[13], lam[13];
+    double sc[52], bs[65];
     ArraySink sk;
-    memcpy(lam, lam_in13, sizeof(lam));
-    switch (m->terr) {
-        case 0: rk4_fwd<4, 0, 0>(mc, 0, X13, u2[0], u2[1], Xn, sk); rk4_bwd_nn<4, 0>(mc, 0, sk, Xn, u2[0], u2[1], lam, acc); break;
-        case 1: rk4_fwd<4, 0, 1>(mc, 0, X13, u2[0], u2[1], Xn, sk); rk4_bwd_nn<4, 1>(mc, 0, sk, Xn, u2[0], u2[1], lam, acc); break;
-        case 2: rk4_fwd<4, 0, 2>(mc, 0, X13, u2[0], u2[1], Xn, sk); rk4_bwd_nn<4, 2>(mc, 0, sk, Xn, u2[0], u2[1], lam, acc); break;
-        default: rk4_fwd<4, 0, 3>(mc, 0, X13, u2[0], u2[1], Xn, sk); rk4_bwd_nn<4, 3>(mc, 0, sk, Xn, u2[0], u2[1], lam, acc); break;
+    Scratch<1> X{sc}, ACC{sc + 13}, TT{sc + 26}, KK{sc + 39}, LAM{bs}, YB{bs + 13}, KB{bs + 26}, XS{bs + 39}, SB{bs + 52};
+    for (int c = 0; c < 13; c++) { X[c] = X13[c]; LAM[c] = lam_in13[c]; }
+    double lam[13];
+#define HC_STEP(TERR)                                                    \
+    {                                                                    \
+        OdeFwdInline<4, 0, TERR> ode{mc, 0, u2[0], u2[1]};                \
+        rk4_fwd(ode, X, ACC, TT, KK, sk);                                 \
+        OdeBwdInline<4, TERR, HostAcc> odeb{mc, 0, u2[0], u2[1], acc};    \
+        rk4_bwd_nn(odeb, sk, sc, LAM, YB, KB, XS, SB);                    \
     }
+    switch (m->terr) {
+        case 0: HC_STEP(0) break;
+        case 1: HC_STEP(1) break;
+        case 2: HC_STEP(2) break;
+        default: HC_STEP(3) break;
+    }
+#undef HC_STEP
+    for (int c = 0; c < 13; c++) lam[c] = LAM[c];
     memcpy(lam_out13, lam, sizeof(lam));
     memcpy(gW104, acc.g, sizeof(acc.g));
 }
