@@ -15,7 +15,10 @@ __global__ void __launch_bounds__(kFwdBlock) ode_kernel(int N, const double* __r
 #pragma unroll
     for (int c = 0; c < 13; c++) X[c] = x[(size_t)live_to_ref(c) * N + n];
     const double ul = u[n], ur = u[(size_t)N + n];
-    ode_fwd<1, TIRE, TERR_DYN>(c_mc, lane0, X, ul, ur, Xd);
+    double ws[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) ws[j] = x[(size_t)(17 + j) * N + n];
+    ode_fwd<1, TIRE, TERR_DYN>(c_mc, lane0, X, ul, ur, Xd, ws);
     if (valid && lane0 == 0) {
 #pragma unroll
         for (int c = 0; c < 13; c++) xd[(size_t)live_to_ref(c) * N + n] = Xd[c];

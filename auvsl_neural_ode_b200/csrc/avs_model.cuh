@@ -670,8 +670,11 @@ AVS_HD void wheel_sign(int i, double& tx, double& ty) {
 // Full ODE:  Xd = f(X; u)      (HybridDynamics::ODE, HybridDynamics.cpp:519-631)
 //   lane0 = first wheel owned by this thread; ul, ur = commanded left / right wheel speeds
 // ------------------------------------------------------------------------------------------------
+//   ws (optional) = the four joint-velocity state entries X[17..20]: the tire models read THOSE as the wheel
+//   speed (HybridDynamics.cpp:384, BekkerDynamics.cpp:68) while the ABA uses the control; inside integrate()
+//   both are equal (VehicleSystem.cpp:132-133), so rollouts pass nullptr.
 template <int WPT, int TIRE, int TERR>
-AVS_HD void ode_fwd(const ModelConst& mc, int lane0, const double X[13], double ul, double ur, double Xd[13]) {
+AVS_HD void ode_fwd(const ModelConst& mc, int lane0, const double X[13], double ul, double ur, double Xd[13], const double* ws = nullptr) {
     double R[9];
     quat_to_R(X, R);
     double S[6] = {0, 0, 0, 0, 0, 0};
@@ -684,11 +687,12 @@ AVS_HD void ode_fwd(const ModelConst& mc, int lane0, const double X[13], double 
         double sink, cv[3], dax, day, cp[3], F[3], C[6];
         WheelAct act;
         wheel_contact<TERR>(mc, tx, ty, R, X, sink, cv, dax, day, cp);
+        const double wsp = ws ? ws[i] : qd;
         if (TIRE == TIRE_NN) {
-            tire_nn_fwd(mc, cv[0], cv[1], qd, sink, F, act.nn);
+            tire_nn_fwd(mc, cv[0], cv[1], wsp, sink, F, act.nn);
             F[2] = fma(kNNDamp, cv[2], F[2]);
         } else {
-            bekker_tire_fwd<TERR>(mc, cv[0], cv[1], qd, sink, cp, F);
+            bekker_tire_fwd<TERR>(mc, cv[0], cv[1], wsp, sink, cp, F);
             F[2] = fma(kBekkerDamp, cv[2], F[2]);
         }
         wheel_aba_fwd(tx, ty, X, qd, F, C, act);

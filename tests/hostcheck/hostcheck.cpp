@@ -44,8 +44,8 @@ static void fill_mc(ModelConst& mc, const double* p416, const double* zw152, con
     mc.grid.x0 = x0; mc.grid.y0 = y0; mc.grid.inv_dx = 1.0 / dx; mc.grid.inv_dy = 1.0 / dy;
 }
 
-template <int TIRE, int TERR> static void ode13(const ModelConst& mc, const double* X13, const double* u, double* Xd13) {
-    ode_fwd<4, TIRE, TERR>(mc, 0, X13, u[0], u[1], Xd13);
+template <int TIRE, int TERR> static void ode13(const ModelConst& mc, const double* X13, const double* u, double* Xd13, const double* ws) {
+    ode_fwd<4, TIRE, TERR>(mc, 0, X13, u[0], u[1], Xd13, ws);
 }
 template <int TIRE, int TERR> static void rk413(const ModelConst& mc, const double* X13, const double* u, double* Xn13, double* stages) {
     ArraySink sink;
@@ -102,9 +102,14 @@ void hc_default_params(double* p416) { for (int k = 0; k < 4; k++) { memcpy(p416
 void hc_aiinv(double* out36) { double A[6][6]; compute_AIinv(A); memcpy(out36, A, sizeof(A)); }
 double hc_tanh(double x) { return tanh_f64(x); }
 
-void hc_ode(const hc_model* m, const double* X13, const double* u2, double* Xd13) {
+void hc_bekker_tire(const hc_model* m, double cvx, double cvy, double w, double sinkage, double* F3) {
     ModelConst mc; mk(m, mc);
-    DISPATCH(ode13, m->tire, m->terr, mc, X13, u2, Xd13);
+    double cp[3] = {0, 0, 0};
+    bekker_tire_fwd<0>(mc, cvx, cvy, w, sinkage, cp, F3);
+}
+void hc_ode(const hc_model* m, const double* X13, const double* u2, double* Xd13, const double* ws4) {
+    ModelConst mc; mk(m, mc);
+    DISPATCH(ode13, m->tire, m->terr, mc, X13, u2, Xd13, ws4);
 }
 void hc_rk4(const hc_model* m, const double* X13, const double* u2, double* Xn13, double* stages52) {
     ModelConst mc; mk(m, mc);

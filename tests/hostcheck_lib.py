@@ -78,10 +78,11 @@ def model(tire=0, terr=0, params=None, height=None, soil=None, x0=0.0, y0=0.0, d
 LIVE = [0, 1, 2, 3, 4, 5, 6, 11, 12, 13, 14, 15, 16]
 
 
-def ode(m, X13, u):
+def ode(m, X13, u, ws4=None):
     X13, u = _f64(X13), _f64(u)
     out = np.zeros(13)
-    lib().hc_ode(C.byref(m), _p(X13), _p(u), _p(out))
+    ws = None if ws4 is None else _f64(ws4)
+    lib().hc_ode(C.byref(m), _p(X13), _p(u), _p(out), None if ws is None else _p(ws))
     return out
 
 

@@ -1,0 +1,147 @@
+"""CPU suite, part 2: the device math (auvsl_neural_ode_b200/csrc/avs_model.cuh + avs_rollout.cuh, the
+templates the sm_100a kernels are built from) compiled by g++ (tests/hostcheck) and checked against the
+oracle: constant-folded ODE / RK4, the hand-written adjoint, rollouts, Bekker model, grid terrain."""
+import os
+
+import numpy as np
+import pytest
+
+import hostcheck_lib as hc
+from oracle import pyoracle as po
+
+P = po.nn_default_params()
+LIVE = hc.LIVE
+
+
+def _golden():
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_v1.npz"))
+
+
+def test_default_weights_match_reference_data():
+    assert np.array_equal(hc.default_params(), P)
+
+
+def test_tanh_accuracy():
+    rng = np.random.default_rng(0)
+    xs = np.concatenate([rng.normal(0, 3, 4000), rng.normal(0, 0.01, 1000), [0.0, 1e-300, 19.9, 30.0, -40.0, 400.0, -1e4]])
+    err = max(abs(hc.lib().hc_tanh(float(x)) - np.tanh(x)) for x in xs)
+    assert err <= 4.5e-16
+
+
+def test_aiinv_is_inverse_of_assembled_inertia():
+    # SURVEY.md Appendix A3 tripwires for AI_b
+    A = np.linalg.inv(hc.aiinv())
+    np.testing.assert_allclose(np.diag(A), [0.4625982159472, 0.5037652562592, 0.5561779557127, 18.43200016022, 18.43200016022, 18.43200016022], rtol=1e-9)
+    assert A[0, 4] == pytest.approx(-1.172867063224, rel=1e-9)
+    assert A[1, 3] == pytest.approx(1.172867063224, rel=1e-9)
+    assert A[1, 5] == pytest.approx(-0.1982760001817, rel=1e-9)
+
+
+@pytest.mark.parametrize("terr", [po.FLAT, po.SLOPE, po.BUMPY])
+def test_ode_and_rk4_vs_golden(terr):
+    G = _golden()
+    m = hc.model(0, terr, P)
+    X, U, Xd, X1 = G[f"ode_nn_X_{terr}"], G[f"ode_nn_U_{terr}"], G[f"ode_nn_Xd_{terr}"], G[f"rk4_nn_X1_{terr}"]
+    for i in range(X.shape[0]):
+        a = hc.ode(m, X[i][LIVE], U[i])
+        np.testing.assert_allclose(a, Xd[i][LIVE], rtol=1e-10, atol=1e-11)
+        b, _ = hc.rk4(m, X[i][LIVE], U[i])
+        np.testing.assert_allclose(b, X1[i][LIVE], rtol=1e-13, atol=1e-14)
+
+
+def test_bekker_ode_vs_golden():
+    G = _golden()
+    m = hc.model(1, po.FLAT, po.bekker_default_params())
+    X, U, Xd = G["ode_bk_X"], G["ode_bk_U"], G["ode_bk_Xd"]
+    for i in range(X.shape[0]):
+        a = hc.ode(m, X[i][LIVE], U[i], X[i][17:21])
+        np.testing.assert_allclose(a, Xd[i][LIVE], rtol=1e-9, atol=1e-9)
+
+
+def test_rollout_vs_golden():
+    G = _golden()
+    m = hc.model(0, po.FLAT, P)
+    xl, xf = hc.rollout(m, G["roll60_x0"], G["roll60_ctrl"], 60)
+    np.testing.assert_allclose(xl, G["roll60_xlist"], rtol=1e-11, atol=1e-13)
+    np.testing.assert_allclose(xf, G["roll60_xfinal"], rtol=1e-11, atol=1e-13)
+    mb = hc.model(0, po.BUMPY, P)
+    xl, _ = hc.rollout(mb, G["bumpy_x0"], G["bumpy_ctrl"], 120)
+    np.testing.assert_allclose(xl, G["bumpy_xlist"], rtol=1e-10, atol=1e-12)
+
+
+def test_bekker_rollout_vs_golden():
+    G = _golden()
+    m = hc.model(1, po.FLAT, po.bekker_default_params())
+    xl, _ = hc.rollout(m, G["bk_x0"], G["bk_ctrl"], 100)
+    np.testing.assert_allclose(xl, G["bk_xlist"], rtol=1e-8, atol=1e-10)
+
+
+def test_hand_adjoint_vs_tape():
+    G = _golden()
+    m = hc.model(0, po.FLAT, P)
+    loss, gps = hc.rollout_grad(m, G["grad20_x0"], G["grad20_ctrl"], G["grad20_gt"], 20)
+    np.testing.assert_allclose(loss, G["grad20_loss"], rtol=1e-11)
+    ref = G["grad20_gps"][:104]
+    # gradient tolerance of the north star: 1e-7 relative; here ~1e-13 of the gradient scale
+    np.testing.assert_allclose(gps, ref, rtol=1e-7, atol=1e-12 * np.abs(ref).max())
+    assert np.all(G["grad20_gps"][104:] == 0)
+
+
+def test_hand_adjoint_T200():
+    G = _golden()
+    m = hc.model(0, po.FLAT, P)
+    loss, gps = hc.rollout_grad(m, G["grad200_x0"], G["grad200_ctrl"], G["grad200_gt"], 200)
+    np.testing.assert_allclose(loss, G["grad200_loss"], rtol=1e-10)
+    ref = G["grad200_gps"][:104]
+    np.testing.assert_allclose(gps, ref, rtol=1e-7, atol=1e-10 * np.abs(ref).max())
+
+
+def test_ode_vjp_matches_finite_differences():
+    rng = np.random.default_rng(3)
+    G = _golden()
+    m = hc.model(0, po.SLOPE, P)
+    X, u = G["ode_nn_X_1"][3][LIVE], G["ode_nn_U_1"][3]
+    lam = rng.normal(size=13)
+    xb, gW = hc.ode_vjp(m, X, u, lam)
+    for c in range(13):
+        h = 1e-7
+        xp, xm = X.copy(), X.copy()
+        xp[c] += h
+        xm[c] -= h
+        fd = lam @ (hc.ode(m, xp, u) - hc.ode(m, xm, u)) / (2 * h)
+        assert fd == pytest.approx(xb[c], rel=2e-5, abs=2e-5 * np.abs(xb).max())
+
+
+def test_grid_terrain_and_soil_vs_oracle():
+    rng = np.random.default_rng(5)
+    n, cell = 40, 0.05
+    x0g = y0g = -0.5 * (n - 1) * cell
+    xs = x0g + cell * np.arange(n)
+    XX, YY = np.meshgrid(xs, xs)
+    h = 0.01 * np.sin(3 * XX + 1.0) * np.cos(2 * YY)
+    d = po.bekker_default_params()
+    soil = np.stack([d[k] * rng.uniform(0.8, 1.2, (n, n)) if k != 3 else rng.uniform(0, 0.1, (n, n)) for k in range(5)])
+    t = po.terrain(po.GRID, height=h, soil=soil, x0=x0g, y0=y0g, dx=cell, dy=cell)
+    G = _golden()
+    # NN on the grid
+    m = hc.model(0, po.GRID, P, height=h, x0=x0g, y0=y0g, dx=cell, dy=cell)
+    for i in range(8):
+        X = G["ode_nn_X_0"][i].copy()
+        X[4:6] = rng.uniform(-0.6, 0.6, 2)
+        a = hc.ode(m, X[LIVE], G["ode_nn_U_0"][i])
+        b = po.ode(po.TIRE_NN, P, t, X, G["ode_nn_U_0"][i])[LIVE]
+        np.testing.assert_allclose(a, b, rtol=1e-10, atol=1e-10)
+    # Bekker with per-cell soil
+    mb = hc.model(1, po.GRID, d, height=h, soil=soil, x0=x0g, y0=y0g, dx=cell, dy=cell)
+    for i in range(8):
+        X = G["ode_bk_X"][i].copy()
+        X[4:6] = rng.uniform(-0.6, 0.6, 2)
+        a = hc.ode(mb, X[LIVE], G["ode_bk_U"][i], X[17:21])
+        b = po.ode(po.TIRE_BEKKER, d, t, X, G["ode_bk_U"][i])[LIVE]
+        np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-9)
+    # gradient through the height field (adjoint of the bilinear lookup)
+    x0, ctrl, gt = G["grad20_x0"], G["grad20_ctrl"], G["grad20_gt"]
+    lo, _, _, _, gps_o = po.rollout_grad_batch(P, t, x0, ctrl, gt, 20, nthreads=2)
+    lh, gps_h = hc.rollout_grad(m, x0, ctrl, gt, 20)
+    np.testing.assert_allclose(lh, lo, rtol=1e-10)
+    np.testing.assert_allclose(gps_h, gps_o[:104], rtol=1e-7, atol=1e-11 * np.abs(gps_o).max())

@@ -1,0 +1,248 @@
+"""GPU suite (-m gpu): the CUDA path through the C ABI (libavsim.so) against the oracle on seeded inputs,
+against the committed golden fixtures, and — at BASELINE.json's full sizes — through size-independent
+properties.  Tolerances are the north star's: states 1e-9 relative, gradients 1e-7 relative.
+Nothing here reads /root/reference."""
+import os
+
+import numpy as np
+import pytest
+
+from auvsl_neural_ode_b200 import capi, synth
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+
+P = po.nn_default_params()
+STATE_RTOL = 1e-9
+GRAD_RTOL = 1e-7
+
+
+def golden():
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_v1.npz"))
+
+
+def rel_state_err(a, b):
+    """1e-9 'relative' for states: relative to max(1, |value|) (angles / positions near 0 are absolute)."""
+    return float(np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b))))
+
+
+@pytest.fixture(scope="module")
+def nn():
+    c = capi.Context(0, capi.TIRE_NN)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def bk():
+    c = capi.Context(0, capi.TIRE_BEKKER)
+    yield c
+    c.close()
+
+
+def test_ode_vs_golden(nn):
+    G = golden()
+    for terr in (capi.FLAT, capi.SLOPE, capi.BUMPY):
+        nn.set_terrain(terr)
+        X, U, Xd = G[f"ode_nn_X_{terr}"], G[f"ode_nn_U_{terr}"], G[f"ode_nn_Xd_{terr}"]
+        got = nn.ode(X.T.copy(), U.T.copy()).T
+        np.testing.assert_allclose(got, Xd, rtol=1e-9, atol=1e-10)
+    nn.set_terrain(capi.FLAT)
+
+
+def test_settle_vs_golden(nn, bk):
+    G = golden()
+    nn.set_terrain(capi.FLAT)
+    nn.set_nn_params(P)
+    assert rel_state_err(nn.settle(), G["settle_nn"]) < STATE_RTOL
+    bk.set_terrain(capi.FLAT)
+    assert rel_state_err(bk.settle(), G["settle_bk"]) < 1e-7  # Bekker: value-dependent branches, looser
+
+
+def test_rollout_vs_golden(nn):
+    G = golden()
+    nn.set_terrain(capi.FLAT)
+    nn.set_nn_params(P)
+    xl, xf = nn.rollout(G["roll60_x0"], G["roll60_ctrl"], 60)
+    assert rel_state_err(xl, G["roll60_xlist"]) < STATE_RTOL
+    assert rel_state_err(xf, G["roll60_xfinal"]) < STATE_RTOL
+    # T = 600 (the reference's m_eval_steps, 5990 RK4 steps): final states
+    _, xf = nn.rollout(G["roll600_x0"], G["roll600_ctrl"], 600, want_list=False)
+    assert rel_state_err(xf, G["roll600_xfinal"]) < STATE_RTOL
+    # Bumpy terrain
+    nn.set_terrain(capi.BUMPY)
+    xl, _ = nn.rollout(G["bumpy_x0"], G["bumpy_ctrl"], 120)
+    assert rel_state_err(xl, G["bumpy_xlist"]) < STATE_RTOL
+    nn.set_terrain(capi.FLAT)
+
+
+def test_rollout_vs_oracle_seeded_ragged_batch(nn):
+    # N not a multiple of the 8 vehicles a warp holds (tail lanes), T small
+    for N, T in ((1, 5), (13, 9), (100, 4)):
+        x0, ctrl, gt = synth.make_batch(N, T, seed=100 + N)
+        xl, xf = nn.rollout(x0, ctrl, T)
+        xl_o, xf_o = po.rollout_batch(po.TIRE_NN, P, po.terrain(po.FLAT), x0, ctrl, T, nthreads=4)
+        assert rel_state_err(xl, xl_o) < STATE_RTOL
+        assert rel_state_err(xf, xf_o) < STATE_RTOL
+
+
+def test_rollout_T1_returns_initial_state(nn):
+    x0, ctrl, _ = synth.make_batch(4, 2, seed=1)
+    xl, xf = nn.rollout(x0, np.zeros((0, 2, 4)), 1)
+    np.testing.assert_array_equal(xf, x0)
+    np.testing.assert_array_equal(xl[0, :21], x0)
+
+
+def test_grad_vs_golden(nn):
+    G = golden()
+    nn.set_terrain(capi.FLAT)
+    nn.set_nn_params(P)
+    loss, red, gps = nn.rollout_grad(G["grad20_x0"], G["grad20_ctrl"], G["grad20_gt"], 20)
+    np.testing.assert_allclose(loss, G["grad20_loss"], rtol=1e-9)
+    scale = np.abs(G["grad20_gps"]).max()
+    np.testing.assert_allclose(gps, G["grad20_gps"], rtol=GRAD_RTOL, atol=1e-11 * scale)
+    np.testing.assert_allclose(red[:416], G["grad20_sum"], rtol=GRAD_RTOL, atol=1e-11 * scale)
+    assert red[417] == 4 and red[416] == pytest.approx(G["grad20_loss"].sum(), rel=1e-9)
+    assert np.all(gps[104:] == 0.0)
+    # the reference's training window (T = 200)
+    loss, red, gps = nn.rollout_grad(G["grad200_x0"], G["grad200_ctrl"], G["grad200_gt"], 200)
+    np.testing.assert_allclose(loss, G["grad200_loss"], rtol=1e-9)
+    scale = np.abs(G["grad200_gps"]).max()
+    np.testing.assert_allclose(gps, G["grad200_gps"], rtol=GRAD_RTOL, atol=1e-9 * scale)
+
+
+def test_grad_vs_oracle_other_terrains_and_params(nn):
+    rng = np.random.default_rng(7)
+    p2 = P.copy()
+    p2[:104] += rng.normal(0, 0.05, 104)
+    p2[104:] = rng.normal(0, 1, 312)  # networks 1..3 are dead parameters
+    nn.set_nn_params(p2)
+    assert np.array_equal(nn.get_nn_params(), p2)
+    for terr in (capi.SLOPE, capi.BUMPY):
+        nn.set_terrain(terr)
+        N, T = 11, 8
+        x0, ctrl, gt = synth.make_batch(N, T, seed=50 + terr)
+        if terr == capi.BUMPY:
+            x0[4] = np.linspace(1.8, 3.7, N)
+        loss, red, gps = nn.rollout_grad(x0, ctrl, gt, T)
+        lo, gs, ls, nk, gps_o = po.rollout_grad_batch(p2, po.terrain(terr), x0, ctrl, gt, T, nthreads=4)
+        np.testing.assert_allclose(loss, lo, rtol=1e-9)
+        np.testing.assert_allclose(gps, gps_o, rtol=GRAD_RTOL, atol=1e-11 * np.abs(gps_o).max())
+    nn.set_terrain(capi.FLAT)
+    nn.set_nn_params(P)
+
+
+def test_explosion_filter_modes(nn):
+    G = golden()
+    x0, ctrl, gt, gps = G["grad20_x0"], G["grad20_ctrl"], G["grad20_gt"], G["grad20_gps"]
+    thresh = float(np.sort(np.abs(gps).max(axis=0))[2]) * 0.999
+    for mode in (0, 1):
+        _, red, _ = nn.rollout_grad(x0, ctrl, gt, 20, explode_thresh=thresh, explode_mode=mode)
+        _, gs, ls, nk, _ = po.rollout_grad_batch(P, po.terrain(po.FLAT), x0, ctrl, gt, 20, explode_thresh=thresh, explode_mode=mode, nthreads=2)
+        assert red[417] == nk
+        np.testing.assert_allclose(red[:416], gs, rtol=GRAD_RTOL, atol=1e-11 * np.abs(gps).max())
+        assert red[416] == pytest.approx(ls, rel=1e-9)
+
+
+def test_checkpoint_chunking_is_transparent(nn):
+    N, T = 600, 6
+    x0, ctrl, gt = synth.make_batch(N, T, seed=77)
+    loss_a, red_a, gps_a = nn.rollout_grad(x0, ctrl, gt, T)
+    per_vehicle = ((T - 1) * 10 * 4 * 14 + 13) * 8
+    nn.set_checkpoint_budget(per_vehicle * 256 + 64)  # forces 256-vehicle chunks: 256 + 256 + 88
+    loss_b, red_b, gps_b = nn.rollout_grad(x0, ctrl, gt, T)
+    nn.set_checkpoint_budget(0)
+    np.testing.assert_array_equal(loss_a, loss_b)
+    np.testing.assert_array_equal(gps_a, gps_b)
+    np.testing.assert_array_equal(red_a, red_b)
+
+
+def test_rmsprop_matches_reference_update(nn):
+    G = golden()
+    nn.set_nn_params(P)
+    nn.reset_optimizer()
+    _, red, _ = nn.rollout_grad(G["grad20_x0"], G["grad20_ctrl"], G["grad20_gt"], 20)
+    nn.rmsprop_step(red)
+    got = nn.get_nn_params()
+    want, _ = po.rmsprop(P, np.ones(416), red[:416] / red[417])
+    np.testing.assert_allclose(got, want, rtol=1e-14, atol=0)
+    assert np.array_equal(got[104:], P[104:])  # zero gradient -> untouched
+    nn.set_nn_params(P)
+    nn.reset_optimizer()
+
+
+def test_bekker_vs_golden(bk):
+    G = golden()
+    bk.set_terrain(capi.FLAT)
+    got = bk.ode(G["ode_bk_X"].T.copy(), G["ode_bk_U"].T.copy()).T
+    np.testing.assert_allclose(got, G["ode_bk_Xd"], rtol=1e-8, atol=1e-8)
+    xl, _ = bk.rollout(G["bk_x0"], G["bk_ctrl"], 100)
+    assert rel_state_err(xl, G["bk_xlist"]) < 1e-7
+
+
+def test_grid_terrain_and_soil(nn, bk):
+    g = synth.make_grid_terrain(n=96)
+    t = po.terrain(po.GRID, height=g["height"], soil=g["soil"], x0=g["x0"], y0=g["y0"], dx=g["dx"], dy=g["dy"])
+    N, T = 9, 12
+    x0, ctrl, gt = synth.make_batch(N, T, seed=31)
+    x0[4], x0[5] = np.linspace(-1.5, 1.5, N), np.linspace(1.0, -1.0, N)
+    nn.set_terrain_grid(g["height"], None, g["x0"], g["y0"], g["dx"], g["dy"])
+    xl, _ = nn.rollout(x0, ctrl, T)
+    xl_o, _ = po.rollout_batch(po.TIRE_NN, P, t, x0, ctrl, T, nthreads=4)
+    assert rel_state_err(xl, xl_o) < STATE_RTOL
+    loss, red, gps = nn.rollout_grad(x0, ctrl, gt, T)
+    lo, _, _, _, gps_o = po.rollout_grad_batch(P, t, x0, ctrl, gt, T, nthreads=4)
+    np.testing.assert_allclose(loss, lo, rtol=1e-9)
+    np.testing.assert_allclose(gps, gps_o, rtol=GRAD_RTOL, atol=1e-11 * np.abs(gps_o).max())
+    nn.set_terrain(capi.FLAT)
+    pb = po.bekker_default_params()
+    bk.set_terrain_grid(g["height"], g["soil"], g["x0"], g["y0"], g["dx"], g["dy"])
+    x0[6] = 0.06
+    xl, _ = bk.rollout(x0, np.clip(ctrl, 1, 8), T)
+    xl_o, _ = po.rollout_batch(po.TIRE_BEKKER, pb, t, x0, np.clip(ctrl, 1, 8), T, nthreads=4)
+    assert rel_state_err(xl, xl_o) < 1e-7
+    bk.set_terrain(capi.FLAT)
+
+
+def test_full_size_properties(nn):
+    """BASELINE configs[1]/[2] sizes (N = 4096): the oracle cannot finish these, so check size-independent
+    properties: permutation equivariance over the batch, determinism, agreement of a strided sample with the
+    oracle, unit quaternions, and linearity of the reduction."""
+    nn.set_terrain(capi.FLAT)
+    nn.set_nn_params(P)
+    N, T = 4096, 200
+    x0, ctrl, gt = synth.make_batch(N, T)
+    loss, red, gps = nn.rollout_grad(x0, ctrl, gt, T)
+    assert np.all(np.isfinite(loss)) and np.all(np.isfinite(gps))
+    assert red[417] == N
+    np.testing.assert_allclose(red[:104], gps[:104].sum(axis=1), rtol=1e-9, atol=1e-9 * np.abs(red[:104]).max())
+    # determinism
+    loss2, red2, gps2 = nn.rollout_grad(x0, ctrl, gt, T)
+    assert np.array_equal(loss, loss2) and np.array_equal(gps, gps2) and np.array_equal(red, red2)
+    # permutation equivariance (a vehicle's result does not depend on its lane / CTA)
+    perm = np.random.default_rng(0).permutation(N)
+    loss_p, _, gps_p = nn.rollout_grad(x0[:, perm].copy(), ctrl[:, :, perm].copy(), gt[:, :, perm].copy(), T)
+    assert np.array_equal(loss_p, loss[perm]) and np.array_equal(gps_p, gps[:, perm])
+    # strided sample against the oracle
+    idx = np.arange(0, N, 1024)
+    lo, _, _, _, gps_o = po.rollout_grad_batch(P, po.terrain(po.FLAT), x0[:, idx].copy(), ctrl[:, :, idx].copy(), gt[:, :, idx].copy(), T, nthreads=4)
+    np.testing.assert_allclose(loss[idx], lo, rtol=1e-9)
+    np.testing.assert_allclose(gps[:, idx], gps_o, rtol=GRAD_RTOL, atol=1e-9 * np.abs(gps_o).max())
+    # forward config: T = 600, final states of a strided sample + unit quaternions everywhere
+    x0, ctrl, gt = synth.make_batch(N, 600)
+    _, xf = nn.rollout(x0, ctrl, 600, want_list=False)
+    np.testing.assert_allclose(np.sqrt((xf[:4] ** 2).sum(axis=0)), 1.0, rtol=0, atol=1e-14)
+    _, xf_o = po.rollout_batch(po.TIRE_NN, P, po.terrain(po.FLAT), x0[:, idx].copy(), ctrl[:, :, idx].copy(), 600, want_list=False, nthreads=4)
+    assert rel_state_err(xf[:, idx], xf_o) < STATE_RTOL
+
+
+def test_argument_errors(nn):
+    with pytest.raises(capi.AvsError):
+        nn.set_terrain(9)
+    x0, ctrl, gt = synth.make_batch(4, 5, seed=1)
+    with pytest.raises(capi.AvsError):
+        nn._ck(capi.lib().avs_rollout(nn._h, 0, 5, 10, None, None, None, None))
+    b = capi.Context(0, capi.TIRE_BEKKER)
+    with pytest.raises(capi.AvsError):
+        b.rollout_grad(x0, ctrl, gt, 5)  # adjoint exists for the NN model only
+    b.close()
