@@ -1,0 +1,60 @@
+// synth_demo.cpp — exercises the drop-in host API end to end without the (private) Jackal logs: writes synthetic
+// Train3/CV3/LD3-style CSV files (linear kinematic model of the reference's scripts/gen_fake_data.py), then runs
+// the same calls as the reference's evaluate.cpp and train.cpp (trainThreads + train) against them.
+#include <cmath>
+#include <cstdio>
+#include <fstream>
+#include <iostream>
+#include <random>
+#include <string>
+
+#include "TestTerrainMaps.h"
+#include "Trainer.h"
+#include "VehicleSystem.h"
+
+static void writeCsv(const std::string& fn, int rows, unsigned seed) {
+    std::mt19937_64 rng(seed);
+    std::uniform_real_distribution<double> U(0, 1);
+    const double B[3][2] = {{0.0472, 0.0438}, {0.0036, -0.0035}, {-0.1744, 0.1748}};
+    const double vbar = 2 + 4 * U(rng), dl = 2 * U(rng) - 1, f = 0.05 + 0.4 * U(rng), ph = 6.28 * U(rng);
+    double x = 0, y = 0, yaw = 0;
+    std::ofstream o(fn);
+    o << ",time,vel_left,vel_right,x,y,yaw,wx,wy,wz,vx,vy\n";
+    o.precision(12);
+    for (int i = 0; i < rows; i++) {
+        const double t = 0.01 * i, vl = vbar + dl + std::sin(6.28 * f * t + ph), vr = vbar - dl + std::sin(6.28 * f * t);
+        const double vx = B[0][0] * vl + B[0][1] * vr, vy = B[1][0] * vl + B[1][1] * vr, wz = B[2][0] * vl + B[2][1] * vr;
+        o << i << "," << t << "," << vl << "," << vr << "," << x << "," << y << "," << yaw << ",0,0," << wz << "," << vx << "," << vy << "\n";
+        for (int k = 0; k < 10; k++) {
+            x += 1e-3 * (std::cos(yaw) * vx - std::sin(yaw) * vy);
+            y += 1e-3 * (std::sin(yaw) * vx + std::cos(yaw) * vy);
+            yaw += 1e-3 * wz;
+        }
+    }
+}
+
+int main(int argc, char** argv) {
+    const std::string dir = argc > 1 ? argv[1] : "/tmp/avsl_synth/";
+    char buf[256];
+    std::snprintf(buf, sizeof(buf), "mkdir -p %s", dir.c_str());
+    if (std::system(buf) != 0) return 2;
+    for (int i = 1; i <= 17; i++) { std::snprintf(buf, sizeof(buf), "%sTrain3_data%02d.csv", dir.c_str(), i); writeCsv(buf, 1300, 100 + i); }
+    std::snprintf(buf, sizeof(buf), "%sLD3_data01.csv", dir.c_str());
+    writeCsv(buf, 2500, 7);
+
+    auto map = std::make_shared<const FlatTerrainMap<ADF>>();
+    auto factory = std::make_shared<VehicleSystemFactory<ADF>>(map);
+    Trainer train(factory, 2);
+    train.setDataDir(dir);
+    train.setParamFile(dir + "tire.net");
+    train.load();
+    train.evaluate_ld3();
+    train.evaluate_train3();
+    for (int it = 0; it < 3; it++) {
+        train.trainThreads();  // one full-batch step over 16 files x 6 windows
+        train.evaluate_validation_dataset();
+    }
+    train.save();
+    std::cout << "synth_demo OK\n";
+    return 0;
+}
