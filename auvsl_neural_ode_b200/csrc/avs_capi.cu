@@ -40,7 +40,7 @@ struct avs_ctx {
     double* d_params = nullptr;  // [416] device copy (RMSProp operates here)
     double* d_sq = nullptr;      // [416] RMSProp state
     bool params_dirty_on_device = false;
-    DevBuf grid_h, grid_s;
+    DevBuf grid_h, grid_s, ztab;
     DevBuf ckpt, gps, loss, reduced, flags, settle;
     DevBuf in_x0, in_ctrl, in_gt, out_list, out_final, io_a, io_b, io_c;
     long long launches = 0;
@@ -135,6 +135,13 @@ int avs_create(avs_ctx** out, int device, int tire_model) {
     for (int i = 0; i < 4 && ok; i++) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_params, sizeof(double) * AVS_NUM_NN_PARAMS) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_sq, sizeof(double) * AVS_NUM_NN_PARAMS) == cudaSuccess;
+    if (ok) {  // constant-fold the fixed z-network into its table
+        std::vector<double> tab((size_t)kZTabN * (kZTabDeg + 1));
+        build_ztab(ctx->mc.Z0, ctx->mc.Z2, ctx->mc.Z4, tab.data());
+        ok = ctx->ztab.reserve(tab.size() * sizeof(double)) == cudaSuccess &&
+             cudaMemcpy(ctx->ztab.p, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess;
+        ctx->mc.ztab = ctx->ztab.as<double>();
+    }
     if (!ok) { avs_destroy(ctx); return AVS_E_CUDA; }
     *out = ctx;
     return avs_reset_optimizer(ctx);
@@ -144,7 +151,7 @@ void avs_destroy(avs_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = {&ctx->grid_h, &ctx->grid_s, &ctx->ckpt, &ctx->gps, &ctx->loss, &ctx->reduced, &ctx->flags, &ctx->settle,
+    DevBuf* bufs[] = {&ctx->grid_h, &ctx->grid_s, &ctx->ztab, &ctx->ckpt, &ctx->gps, &ctx->loss, &ctx->reduced, &ctx->flags, &ctx->settle,
                       &ctx->in_x0, &ctx->in_ctrl, &ctx->in_gt, &ctx->out_list, &ctx->out_final, &ctx->io_a, &ctx->io_b, &ctx->io_c};
     for (DevBuf* b : bufs) b->release();
     if (ctx->d_params) cudaFree(ctx->d_params);

@@ -85,6 +85,7 @@ struct ModelConst {
     double AIinv[6][6];                   // (I_b + sum X^T Ia X)^-1
     double bek[5];                        // Bekker soil 5-vector as passed to setParams (BekkerDynamics.cpp:12-21)
     GridTerrain grid;
+    const double* ztab;                   // [kZTabN][kZTabDeg+1] piecewise polynomial of the fixed z-net (build_ztab)
     int terr_kind;                        // used by the TERR_DYN instantiations
 };
 
@@ -310,48 +311,122 @@ template <int TERR> AVS_HD double altitude(const ModelConst& mc, double x, doubl
 // ------------------------------------------------------------------------------------------------
 // Tire network (TireNetwork.cpp:54-119), network 0.  Activations are kept for the adjoint.
 // ------------------------------------------------------------------------------------------------
+// ---- the fixed z-branch as a table ---------------------------------------------------------------
+// z4(s0) = Z4 . tanh(Z2 tanh(Z0 s0)) has CONSTANT weights (TireNetwork.cpp:17-32; they are not in the
+// trainable parameter vector, :130-161) and a scalar input (the scaled sinkage), i.e. it is one fixed analytic
+// odd function of one variable.  The reference re-evaluates its 16 tanh per wheel per ODE call; here it is
+// constant-folded like AI^-1: a piecewise degree-9 polynomial on 832 uniform intervals of width 1/16 over
+// s0 in [0, 52] (beyond which every first-layer unit is saturated and z4 is constant to 1.5e-16), built at
+// context creation in long double (build_ztab).  Interpolation error < 1e-16 relative (tests).  For s0 <= 0,
+// z4 <= 0 and relu gives exactly 0 with zero derivative, as CondExpGt does.
+constexpr int kZTabDeg = 9, kZTabPerUnit = 16, kZTabN = 832;
+constexpr double kZTabSMax = (double)kZTabN / kZTabPerUnit;
+
+AVS_HD double ztab_eval(const double* tab, double s0, double* dz /* d z4 / d s0, or nullptr */) {
+    const double sc = s0 < kZTabSMax ? s0 : kZTabSMax;
+    const double u = sc * (double)kZTabPerUnit;
+    int i = (int)u;
+    i = i > kZTabN - 1 ? kZTabN - 1 : i;
+    const double x = fma(u - (double)i, 2.0, -1.0);
+    const double* c = tab + (size_t)i * (kZTabDeg + 1);
+    double cc[kZTabDeg + 1];
+#pragma unroll
+    for (int k = 0; k <= kZTabDeg; k++) {
+#if defined(__CUDA_ARCH__)
+        cc[k] = __ldg(c + k);
+#else
+        cc[k] = c[k];
+#endif
+    }
+    double p = cc[kZTabDeg], d = 0.0;
+    if (dz) {
+#pragma unroll
+        for (int k = kZTabDeg - 1; k >= 0; k--) { d = fma(d, x, p); p = fma(p, x, cc[k]); }
+        *dz = s0 < kZTabSMax ? d * (2.0 * kZTabPerUnit) : 0.0;
+    } else {
+#pragma unroll
+        for (int k = kZTabDeg - 1; k >= 0; k--) p = fma(p, x, cc[k]);
+    }
+    return p;
+}
+
+// host-side construction (long double): Chebyshev-node interpolation per interval, converted to monomials in x in [-1,1]
+inline void build_ztab(const double Z0[8], const double Z2[8][8], const double Z4[8], double* tab) {
+    const int n = kZTabDeg + 1;
+    const long double PI = 3.14159265358979323846264338327950288L;
+    // monomial coefficients of the Chebyshev polynomials T_0..T_9
+    long double Tm[kZTabDeg + 1][kZTabDeg + 1] = {{0}};
+    Tm[0][0] = 1;
+    Tm[1][1] = 1;
+    for (int k = 2; k < n; k++)
+        for (int j = 0; j < n; j++) Tm[k][j] = (j > 0 ? 2 * Tm[k - 1][j - 1] : 0) - Tm[k - 2][j];
+    for (int i = 0; i < kZTabN; i++) {
+        const long double a = (long double)i / kZTabPerUnit, b = (long double)(i + 1) / kZTabPerUnit;
+        long double fx[kZTabDeg + 1], xs[kZTabDeg + 1];
+        for (int k = 0; k < n; k++) {
+            xs[k] = cosl(PI * (2 * k + 1) / (2 * n));
+            const long double sv = (a + b) / 2 + (b - a) / 2 * xs[k];
+            long double g0[8], z = 0;
+            for (int j = 0; j < 8; j++) g0[j] = tanhl((long double)Z0[j] * sv);
+            for (int j = 0; j < 8; j++) {
+                long double acc = 0;
+                for (int q = 0; q < 8; q++) acc += (long double)Z2[j][q] * g0[q];
+                z += (long double)Z4[j] * tanhl(acc);
+            }
+            fx[k] = z;
+        }
+        long double mono[kZTabDeg + 1] = {0};
+        for (int m = 0; m < n; m++) {  // Chebyshev coefficient a_m
+            long double am = 0;
+            for (int k = 0; k < n; k++) am += fx[k] * cosl(PI * m * (2 * k + 1) / (2 * n));
+            am *= (m == 0 ? 1.0L : 2.0L) / n;
+            for (int j = 0; j < n; j++) mono[j] += am * Tm[m][j];
+        }
+        for (int j = 0; j < n; j++) tab[(size_t)i * n + j] = (double)mono[j];
+    }
+}
+
 struct NNAct {
     double s1, s2, s3;  // scaled xy features
-    double h0[8], h2[8], g0[8], g2[8];
-    double z4;
+    double h0[8], h2[8];
+    double z4, dz4;     // z-branch value and its derivative w.r.t. the scaled sinkage
 };
 
 // in: contact velocity (vx, vy), wheel speed w, sinkage zr -> (Fx, Fy, Fz) before the damping term.
 // Loop nests are ordered so that consecutive instructions belong to different accumulators (ILP).
+template <bool WANT_D = false>
 AVS_HD void tire_nn_fwd(const ModelConst& mc, double vx, double vy, double w, double zr, double F[3], NNAct& a) {
     const double s0 = zr * (1.0 / kInStd0);
     a.s1 = (w * kTireRadius - vx) * (1.0 / kInStd1);
     a.s2 = w * (1.0 / kInStd2);
     a.s3 = vy * (1.0 / kInStd3);
+    // z-branch (table); issued first so that its loads overlap the xy-net
+    a.dz4 = 0.0;
+    const double z4 = s0 > 0.0 ? ztab_eval(mc.ztab, s0, WANT_D ? &a.dz4 : nullptr) : 0.0;
+    a.z4 = z4;
 #pragma unroll
-    for (int j = 0; j < 8; j++) { a.h0[j] = mc.W0[j][0] * a.s1; a.g0[j] = mc.Z0[j] * s0; }
+    for (int j = 0; j < 8; j++) a.h0[j] = mc.W0[j][0] * a.s1;
 #pragma unroll
     for (int j = 0; j < 8; j++) a.h0[j] = fma(mc.W0[j][1], a.s2, a.h0[j]);
 #pragma unroll
     for (int j = 0; j < 8; j++) a.h0[j] = fma(mc.W0[j][2], a.s3, a.h0[j]);
     tanh_vec<8>(a.h0);
-    tanh_vec<8>(a.g0);
 #pragma unroll
-    for (int j = 0; j < 8; j++) { a.h2[j] = mc.W2[j][0] * a.h0[0]; a.g2[j] = mc.Z2[j][0] * a.g0[0]; }
+    for (int j = 0; j < 8; j++) a.h2[j] = mc.W2[j][0] * a.h0[0];
 #pragma unroll
     for (int k = 1; k < 8; k++) {
 #pragma unroll
-        for (int j = 0; j < 8; j++) { a.h2[j] = fma(mc.W2[j][k], a.h0[k], a.h2[j]); a.g2[j] = fma(mc.Z2[j][k], a.g0[k], a.g2[j]); }
+        for (int j = 0; j < 8; j++) a.h2[j] = fma(mc.W2[j][k], a.h0[k], a.h2[j]);
     }
     tanh_vec<8>(a.h2);
-    tanh_vec<8>(a.g2);
-    // three output rows, each as two interleaved partial sums
+    // two output rows, each as two interleaved partial sums
     double f0a = mc.W4[0][0] * a.h2[0], f0b = mc.W4[0][1] * a.h2[1];
     double f1a = mc.W4[1][0] * a.h2[0], f1b = mc.W4[1][1] * a.h2[1];
-    double z4a = mc.Z4[0] * a.g2[0], z4b = mc.Z4[1] * a.g2[1];
 #pragma unroll
     for (int k = 2; k < 8; k += 2) {
         f0a = fma(mc.W4[0][k], a.h2[k], f0a); f0b = fma(mc.W4[0][k + 1], a.h2[k + 1], f0b);
         f1a = fma(mc.W4[1][k], a.h2[k], f1a); f1b = fma(mc.W4[1][k + 1], a.h2[k + 1], f1b);
-        z4a = fma(mc.Z4[k], a.g2[k], z4a);    z4b = fma(mc.Z4[k + 1], a.g2[k + 1], z4b);
     }
-    const double z4 = z4a + z4b;
-    a.z4 = z4;
     F[0] = (f0a + f0b) * kOutStd0;
     F[1] = (f1a + f1b) * kOutStd1;
     F[2] = (z4 > 0.0 ? z4 : 0.0) * kOutStd2;  // relu = CondExpGt(x,0,x,0) (TireNetwork.cpp:47-50)
@@ -362,26 +437,26 @@ template <class Acc>
 AVS_HD void tire_nn_bwd(const ModelConst& mc, const NNAct& a, const double Fbar[3], double& vxb, double& vyb, double& zrb, Acc& acc) {
     const double o0 = Fbar[0] * kOutStd0, o1 = Fbar[1] * kOutStd1;
     const double oz = (a.z4 > 0.0) ? Fbar[2] * kOutStd2 : 0.0;  // CondExpGt: derivative 0 at z4 <= 0
-    double d2[8], e2[8];
+    double d2[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         acc.fma(kOffW4 + k, o0, a.h2[k]);
         acc.fma(kOffW4 + 8 + k, o1, a.h2[k]);
     }
 #pragma unroll
-    for (int k = 0; k < 8; k++) { d2[k] = fma(mc.W4[1][k], o1, mc.W4[0][k] * o0); e2[k] = mc.Z4[k] * oz; }
+    for (int k = 0; k < 8; k++) d2[k] = fma(mc.W4[1][k], o1, mc.W4[0][k] * o0);
 #pragma unroll
-    for (int k = 0; k < 8; k++) { d2[k] *= fma(-a.h2[k], a.h2[k], 1.0); e2[k] *= fma(-a.g2[k], a.g2[k], 1.0); }
-    double d0[8], e0[8];
+    for (int k = 0; k < 8; k++) d2[k] *= fma(-a.h2[k], a.h2[k], 1.0);
+    double d0[8];
 #pragma unroll
-    for (int k = 0; k < 8; k++) { d0[k] = mc.W2[0][k] * d2[0]; e0[k] = mc.Z2[0][k] * e2[0]; }
+    for (int k = 0; k < 8; k++) d0[k] = mc.W2[0][k] * d2[0];
 #pragma unroll
     for (int j = 1; j < 8; j++) {
 #pragma unroll
-        for (int k = 0; k < 8; k++) { d0[k] = fma(mc.W2[j][k], d2[j], d0[k]); e0[k] = fma(mc.Z2[j][k], e2[j], e0[k]); }
+        for (int k = 0; k < 8; k++) d0[k] = fma(mc.W2[j][k], d2[j], d0[k]);
     }
 #pragma unroll
-    for (int k = 0; k < 8; k++) { d0[k] *= fma(-a.h0[k], a.h0[k], 1.0); e0[k] *= fma(-a.g0[k], a.g0[k], 1.0); }
+    for (int k = 0; k < 8; k++) d0[k] *= fma(-a.h0[k], a.h0[k], 1.0);
 #pragma unroll
     for (int j = 0; j < 8; j++) {
 #pragma unroll
@@ -395,17 +470,15 @@ AVS_HD void tire_nn_bwd(const ModelConst& mc, const NNAct& a, const double Fbar[
     }
     double s1a = mc.W0[0][0] * d0[0], s1b = mc.W0[1][0] * d0[1];
     double s3a = mc.W0[0][2] * d0[0], s3b = mc.W0[1][2] * d0[1];
-    double s0a = mc.Z0[0] * e0[0], s0b = mc.Z0[1] * e0[1];
 #pragma unroll
     for (int j = 2; j < 8; j += 2) {
         s1a = fma(mc.W0[j][0], d0[j], s1a); s1b = fma(mc.W0[j + 1][0], d0[j + 1], s1b);
         s3a = fma(mc.W0[j][2], d0[j], s3a); s3b = fma(mc.W0[j + 1][2], d0[j + 1], s3b);
-        s0a = fma(mc.Z0[j], e0[j], s0a);    s0b = fma(mc.Z0[j + 1], e0[j + 1], s0b);
     }
     // wheel speed (s2) is a control, not differentiated
     vxb = -(s1a + s1b) * (1.0 / kInStd1);
     vyb = (s3a + s3b) * (1.0 / kInStd3);
-    zrb = (s0a + s0b) * (1.0 / kInStd0);
+    zrb = (oz * a.dz4) * (1.0 / kInStd0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -726,7 +799,7 @@ AVS_HD void ode_bwd_nn(const ModelConst& mc, int lane0, const double X[13], doub
         double sink, cv[3], dax, day, cp[3], F[3], C[6], Fb[3];
         WheelAct act;
         wheel_contact<TERR>(mc, tx, ty, R, X, sink, cv, dax, day, cp);
-        tire_nn_fwd(mc, cv[0], cv[1], qd, sink, F, act.nn);
+        tire_nn_fwd<true>(mc, cv[0], cv[1], qd, sink, F, act.nn);
         F[2] = fma(kNNDamp, cv[2], F[2]);
         wheel_aba_fwd(tx, ty, X, qd, F, C, act);
         wheel_aba_bwd(tx, ty, qd, act, Sb, Fb, wb, vb);

@@ -40,6 +40,8 @@ static void fill_mc(ModelConst& mc, const double* p416, const double* zw152, con
     if (bek5) memcpy(mc.bek, bek5, sizeof(mc.bek));
     compute_AIinv(mc.AIinv);
     mc.terr_kind = 0;
+    static std::vector<double> ztab;
+    if (zw152) { ztab.resize((size_t)kZTabN * (kZTabDeg + 1)); build_ztab(mc.Z0, mc.Z2, mc.Z4, ztab.data()); mc.ztab = ztab.data(); }
     mc.grid.height = height; mc.grid.soil = soil; mc.grid.nx = nx; mc.grid.ny = ny;
     mc.grid.x0 = x0; mc.grid.y0 = y0; mc.grid.inv_dx = 1.0 / dx; mc.grid.inv_dy = 1.0 / dy;
 }
@@ -101,6 +103,11 @@ void hc_zweights(double* out152) { memcpy(out152, kFixedZ0, 64); memcpy(out152 +
 void hc_default_params(double* p416) { for (int k = 0; k < 4; k++) { memcpy(p416 + 104 * k, kDefaultW0, 192); memcpy(p416 + 104 * k + 24, kDefaultW2, 512); memcpy(p416 + 104 * k + 88, kDefaultW4, 128); } }
 void hc_aiinv(double* out36) { double A[6][6]; compute_AIinv(A); memcpy(out36, A, sizeof(A)); }
 double hc_tanh(double x) { return tanh_f64(x); }
+double hc_ztab(double s0, double* dz) {
+    static std::vector<double> t;
+    if (t.empty()) { t.resize((size_t)kZTabN * (kZTabDeg + 1)); build_ztab((const double*)kFixedZ0, (const double(*)[8])kFixedZ2, (const double*)kFixedZ4, t.data()); }
+    return ztab_eval(t.data(), s0, dz);
+}
 
 void hc_bekker_tire(const hc_model* m, double cvx, double cvy, double w, double sinkage, double* F3) {
     ModelConst mc; mk(m, mc);
