@@ -324,8 +324,8 @@ int avs_rollout_grad_dev(avs_ctx* ctx, int N, int T, int substeps, const double*
     const size_t n = (size_t)N;
     if (!d_loss) { CK(ctx->loss.reserve(n * 8)); d_loss = ctx->loss.as<double>(); }
     if (!d_grad_live) { CK(ctx->gps.reserve((size_t)kNumLive * n * 8)); d_grad_live = ctx->gps.as<double>(); }
-    // checkpoint buffer: S*4*14 + 13 doubles per vehicle; process the batch in chunks if it does not fit the budget
-    const size_t per_vehicle = ((size_t)(T - 1) * substeps * 4 * kCkRows + 13) * 8;
+    // checkpoint buffer: (S*4 + 1) records of 14 doubles per vehicle; process the batch in chunks if it does not fit the budget
+    const size_t per_vehicle = ((size_t)(T - 1) * substeps * 4 + 1) * kCkRows * 8;
     size_t budget = ctx->ckpt_budget;
     if (budget == 0) {
         size_t free_b = 0, total_b = 0;

@@ -47,6 +47,7 @@ template <int BLOCK> struct SmemAcc {
 // SB = (df/dX)^T KB at XS, dL/dW += ...
 template <int TERR, int BLOCK>
 __device__ __noinline__ void ode_bwd_call(int lane0, int slotXS, int slotKB, int slotSB, int slotG, double ul, double ur) {
+    // (slotXS is dynamic: the record buffers alternate)
     const Scratch<BLOCK> XS = scratch_col<BLOCK>(slotXS), KB = scratch_col<BLOCK>(slotKB), SB = scratch_col<BLOCK>(slotSB);
     SmemAcc<BLOCK> acc{g_smem + slotG * BLOCK + threadIdx.x};
     double X[13], Xb[13];
@@ -59,8 +60,45 @@ __device__ __noinline__ void ode_bwd_call(int lane0, int slotXS, int slotKB, int
 template <int TERR, int BLOCK> struct OdeBwdCall {
     int lane0, slotXS, slotKB, slotSB, slotG;
     double ul, ur;
-    __device__ __forceinline__ void operator()(Scratch<BLOCK>, Scratch<BLOCK>, Scratch<BLOCK>) const {
-        ode_bwd_call<TERR, BLOCK>(lane0, slotXS, slotKB, slotSB, slotG, ul, ur);
+    int slotXB;  // second record buffer
+    __device__ __forceinline__ void operator()(Scratch<BLOCK> XS, Scratch<BLOCK>, Scratch<BLOCK>) const {
+        const bool isA = XS.p == scratch_col<BLOCK>(slotXS).p;
+        ode_bwd_call<TERR, BLOCK>(lane0, isA ? slotXS : slotXB, slotKB, slotSB, slotG, ul, ur);
+    }
+};
+
+// Reverse record stream with one-record-ahead prefetch: while the adjoint of stage s runs (~8 k cycles), the
+// record of the stage before it is copied HBM -> this lane's shared-memory column by cp.async (LDGSTS), so the
+// HBM latency of the checkpoint stream is off the critical path of the single resident warp.
+template <int BLOCK> struct CkptStreamAsync {
+    const double* rec;   // current record in HBM
+    size_t stride;
+    long remaining;      // records before the current one
+    int slotA, slotB, parity;
+    __device__ __forceinline__ Scratch<BLOCK> cur() const { return scratch_col<BLOCK>(parity ? slotB : slotA); }
+    __device__ __forceinline__ void prefetch_prev() {
+        if (remaining <= 0) return;
+        const double* src = rec - (size_t)kCkRows * stride;
+        const Scratch<BLOCK> dst = scratch_col<BLOCK>(parity ? slotA : slotB);
+#pragma unroll
+        for (int c = 0; c < kCkRows; c++) {
+            const unsigned saddr = (unsigned)__cvta_generic_to_shared(&dst[c]);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(src + (size_t)c * stride) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    __device__ __forceinline__ void init() {  // synchronous load of the final-state record, then start the pipeline
+        const Scratch<BLOCK> dst = cur();
+#pragma unroll
+        for (int c = 0; c < kCkRows; c++) dst[c] = __ldg(rec + (size_t)c * stride);
+        prefetch_prev();
+    }
+    __device__ __forceinline__ void advance() {
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        parity ^= 1;
+        rec -= (size_t)kCkRows * stride;
+        remaining--;
+        prefetch_prev();
     }
 };
 

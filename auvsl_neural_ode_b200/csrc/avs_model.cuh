@@ -891,24 +891,30 @@ AVS_HD void rk4_fwd(Ode& ode, St X, St ACC, St T, St K, Sink& sink) {
     sink.finish(inv);
 }
 
-// Adjoint of one RK4 step.  src.load(s, XS, inv) fills the scratch column XS with stage input s and returns
-// the inverse norm stored with it (s = 0: the inverse norm of the step output, also via load_inv);
-// Xnq = quaternion of the step's (normalised) output.  `odeb(XS, KB, SB)` computes SB = (df/dX)^T KB at
-// stage input XS (and accumulates the weight gradient).  LAM (13, in/out) = adjoint of the step output on
-// entry, adjoint of the step input on return; YB, KB, XS, SB are scratch columns.
-template <class OdeB, class Src, class St>
-AVS_HD void rk4_bwd_nn(OdeB& odeb, Src& src, const double Xnq[4], St LAM, St YB, St KB, St XS, St SB) {
+// Adjoint of one RK4 step over a reverse RECORD STREAM.  The forward sweep stores, per RK4 step, four records
+// (one per stage): 13 state entries + slot 13.  Slot 13 of a stage-s record (s = 1..3) holds the inverse norm
+// that produced that stage input; slot 13 of a stage-0 record holds the inverse norm of the PREVIOUS step's final
+// normalisation (so that the record that serves as "state after the step" also delivers that step's norm).
+// On entry st.cur() is the record after this step; st.advance() steps to the previous record (and prefetches the
+// one before it).  `odeb(XS, KB, SB)`: SB = (df/dX)^T KB at stage input XS (+ weight-gradient accumulation).
+// LAM (13, in/out) = adjoint of the step output on entry, adjoint of the step input on return.
+template <class OdeB, class Stream, class St>
+AVS_HD void rk4_bwd_nn(OdeB& odeb, Stream& st, St LAM, St YB, St KB, St SB) {
     const double h = kDt;
-    double inv_s;
-    src.load_inv(0, inv_s);
-    renorm_bwd(Xnq, inv_s, LAM);  // adjoint of Y+ = X + h/6 (k1 + 2k2 + 2k3 + k4) through the final normalisation
+    {
+        const St XN = st.cur();
+        const double inv_n = XN[13];
+        renorm_bwd(XN, inv_n, LAM);  // adjoint of Y+ = X + h/6 (k1 + 2k2 + 2k3 + k4) through the final normalisation
+    }
 #pragma unroll
     for (int c = 0; c < 13; c++) { const double l = LAM[c]; YB[c] = l; KB[c] = (h / 6.0) * l; }
 #pragma unroll 1
     for (int s = 3; s >= 0; s--) {
-        src.load(s, XS, inv_s);
+        st.advance();
+        const St XS = st.cur();
         odeb(XS, KB, SB);
         if (s > 0) {
+            const double inv_s = XS[13];
             renorm_bwd(XS, inv_s, SB);  // stage input s = N(X + c_s k_s)
             const double cs = (s == 3) ? h : .5 * h;
             const double wk = (s == 1) ? (h / 6.0) : (h / 3.0);  // weight of k_s in the output combination

@@ -11,9 +11,9 @@
 //   ctrl    [T-1][2][N]      (vl, vr) applied during macro step i -> i+1 (= traj[i].vl/vr, Trainer.cpp:564-565)
 //   x_list  [T][23][N]       optional: the reference's x_list (row 0 = x0 + controls of row 0)
 //   x_final [21][N]          optional
-//   ckpt    [S*4][14][Nc] + [13][Nc]   stage inputs of every RK4 step (S = (T-1)*substeps), each with the
-//                            inverse quaternion norm that produced it, + the final state: what the reverse
-//                            sweep needs instead of a tape (448 B per vehicle-step)
+//   ckpt    [S*4+1][14][Nc]  one record per RK4 stage (S = (T-1)*substeps steps) + one for the final state:
+//                            13 state entries + the inverse quaternion norm the reverse sweep needs with it.
+//                            This stream replaces the tape (448 B per vehicle-step)
 //   gt      [T][3][N]        (yaw, x, y) ground truth rows
 //   loss    [N], gps [104][N] per-sample loss and gradient w.r.t. the live tire-network weights
 #pragma once
@@ -47,7 +47,7 @@ constexpr int kCkRows = 14;  // 13 live states + 1 inverse norm per stage record
 
 // writes stage records straight to HBM (only the writer lane of a group stores)
 struct CkptSink {
-    double* base;  // &ckpt[step][0][0][n]
+    double* base;  // &ckpt[step*4][0][n]
     size_t stride; // Nc
     bool on;
     template <class V> AVS_HD void stage(int s, const V& T, double inv) {
@@ -57,20 +57,24 @@ struct CkptSink {
         for (int c = 0; c < 13; c++) p[(size_t)c * stride] = T[c];
         if (s > 0) p[(size_t)13 * stride] = inv;
     }
+    // the inverse norm of this step's final normalisation rides in slot 13 of the NEXT record (stage 0 of the
+    // next step, or the final-state record)
     AVS_HD void finish(double inv) {
-        if (on) base[(size_t)13 * stride] = inv;  // stage 0 record carries the inverse norm of the step output
+        if (on) base[((size_t)4 * kCkRows + 13) * stride] = inv;
     }
 };
-struct CkptSrc {
-    const double* base;
+
+// reverse record stream on the host / generic path: plain loads, no prefetch
+template <class St> struct CkptStreamSimple {
+    const double* rec;  // current record in HBM
     size_t stride;
-    template <class V> AVS_HD void load(int s, V&& St, double& inv) const {
-        const double* p = base + (size_t)s * kCkRows * stride;
+    St buf;             // 14-slot scratch column
+    AVS_HD void load() {
 #pragma unroll
-        for (int c = 0; c < 13; c++) St[c] = ld(p + (size_t)c * stride);
-        inv = ld(p + (size_t)13 * stride);
+        for (int c = 0; c < kCkRows; c++) buf[c] = ld(rec + (size_t)c * stride);
     }
-    AVS_HD void load_inv(int s, double& inv) const { inv = ld(base + ((size_t)s * kCkRows + 13) * stride); }
+    AVS_HD St cur() const { return buf; }
+    AVS_HD void advance() { rec -= (size_t)kCkRows * stride; load(); }
 };
 
 // live-state index -> reference 21-state index
@@ -141,16 +145,17 @@ AVS_HD void rollout_fwd_body(const RolloutArgs& a, int n, int lane0, bool valid,
     }
 }
 
-constexpr int kBwdScratch = 65;  // LAM[13] | YB[13] | KB[13] | XS[13] | SB[13]
+constexpr int kBwdScratch = 80;  // LAM[13] | YB[13] | KB[13] | SB[13] | record buffer A[14] | record buffer B[14]
 
 // Reverse sweep over the checkpoints written by rollout_fwd_body<.., STORE=true>.
 //   L = (sum_{i=1}^{T-1} l_i) / T / traj_len   (Trainer.cpp:612-649)
-// mk_odeb(ul, ur) returns the functor SB = (df/dX)^T KB at XS (accumulating dL/dW)
-template <class MkOdeB, class St>
-AVS_HD void rollout_bwd_body(const RolloutArgs& a, int n, double& loss_out, St S, MkOdeB mk_odeb) {
-    const size_t N = (size_t)a.N, NK = (size_t)a.Nc;
+// mk_odeb(ul, ur) returns the functor SB = (df/dX)^T KB at XS (accumulating dL/dW); `st` is the reverse record
+// stream positioned (and loaded) at the final-state record.
+template <class MkOdeB, class Stream, class St>
+AVS_HD void rollout_bwd_body(const RolloutArgs& a, int n, double& loss_out, St S, Stream& st, MkOdeB mk_odeb) {
+    const size_t N = (size_t)a.N;
     const int T = a.T;
-    St LAM = S, YB = S.sub(13), KB = S.sub(26), XS = S.sub(39), SB = S.sub(52);
+    St LAM = S, YB = S.sub(13), KB = S.sub(26), SB = S.sub(39);
     // traj_len = sum |d(x,y)_gt| ; 0 -> 1   (Trainer.cpp:635-647)
     double traj_len = 0.0;
     {
@@ -166,14 +171,14 @@ AVS_HD void rollout_bwd_body(const RolloutArgs& a, int n, double& loss_out, St S
     const double seed = 1.0 / (double)T / traj_len;
 #pragma unroll
     for (int c = 0; c < 13; c++) LAM[c] = 0.0;
-    // record holding the state AFTER the step being reversed: the next step's stage-0 record, or the final state
-    const double* next = a.ckpt + ((size_t)(T - 1) * a.substeps * 4) * kCkRows * NK + n;
     double lsum = 0.0;
     for (int i = T - 1; i >= 1; i--) {
         {
+            // st.cur() = state of data row i (the state after the step about to be reversed)
+            const St XR = st.cur();
             double Xr[13], lam[13];
 #pragma unroll
-            for (int c = 0; c < 13; c++) { Xr[c] = ld(next + (size_t)c * NK); lam[c] = 0.0; }
+            for (int c = 0; c < 13; c++) { Xr[c] = XR[c]; lam[c] = 0.0; }
             const double yaw_gt = ld(a.gt + ((size_t)i * 3 + 0) * N + n);
             const double x_gt = ld(a.gt + ((size_t)i * 3 + 1) * N + n);
             const double y_gt = ld(a.gt + ((size_t)i * 3 + 2) * N + n);
@@ -185,15 +190,7 @@ AVS_HD void rollout_bwd_body(const RolloutArgs& a, int n, double& loss_out, St S
         const double ur = ld(a.ctrl + ((size_t)(i - 1) * 2 + 1) * N + n);
         auto odeb = mk_odeb(ul, ur);
 #pragma unroll 1
-        for (int s = a.substeps - 1; s >= 0; s--) {
-            const double* rec = a.ckpt + ((size_t)((size_t)(i - 1) * a.substeps + s) * 4) * kCkRows * NK + n;
-            CkptSrc src{rec, NK};
-            double Xnq[4];
-#pragma unroll
-            for (int c = 0; c < 4; c++) Xnq[c] = ld(next + (size_t)c * NK);
-            rk4_bwd_nn(odeb, src, Xnq, LAM, YB, KB, XS, SB);
-            next = rec;
-        }
+        for (int s = a.substeps - 1; s >= 0; s--) rk4_bwd_nn(odeb, st, LAM, YB, KB, SB);
     }
     loss_out = lsum * seed;
 }

@@ -14,8 +14,6 @@ struct ArraySink {
     double St[4][13], inv[4];
     template <class V> void stage(int s, const V& T, double i) { for (int c = 0; c < 13; c++) St[s][c] = T[c]; if (s > 0) inv[s] = i; }
     void finish(double i) { inv[0] = i; }
-    template <class V> void load(int s, V&& out, double& i) const { for (int c = 0; c < 13; c++) out[c] = St[s][c]; i = inv[s]; }
-    void load_inv(int s, double& i) const { i = inv[s]; }
 };
 
 struct HostAcc {
@@ -80,7 +78,10 @@ template <int TIRE, int TERR> static void fwd_body(const ModelConst& mc, const R
 template <int TERR> static void bwd_body(const ModelConst& mc, const RolloutArgs& a, int n, HostAcc& acc, double& loss) {
     double sc[kBwdScratch];
     auto mk = [&mc, &acc](double ul, double ur) { return OdeBwdInline<4, TERR, HostAcc>{mc, 0, ul, ur, acc}; };
-    rollout_bwd_body(a, n, loss, Scratch<1>{sc}, mk);
+    const size_t nrec = (size_t)(a.T - 1) * a.substeps * 4;
+    CkptStreamSimple<Scratch<1>> st{a.ckpt + nrec * kCkRows * a.Nc + n, (size_t)a.Nc, Scratch<1>{sc + 52}};
+    st.load();
+    rollout_bwd_body(a, n, loss, Scratch<1>{sc}, st, mk);
 }
 
 extern "C" {
@@ -137,33 +138,6 @@ void hc_ode_vjp(const hc_model* m, const double* X13, const double* u2, const do
     }
     memcpy(gW104, acc.g, sizeof(acc.g));
 }
-// vector-Jacobian product of one RK4 step
-void hc_rk4_vjp(const hc_model* m, const double* X13, const double* u2, const double* lam_in13, double* lam_out13, double* gW104) {
-    ModelConst mc; mk(m, mc);
-    HostAcc acc;
-    double sc[52], bs[65];
-    ArraySink sk;
-    Scratch<1> X{sc}, ACC{sc + 13}, TT{sc + 26}, KK{sc + 39}, LAM{bs}, YB{bs + 13}, KB{bs + 26}, XS{bs + 39}, SB{bs + 52};
-    for (int c = 0; c < 13; c++) { X[c] = X13[c]; LAM[c] = lam_in13[c]; }
-    double lam[13];
-#define HC_STEP(TERR)                                                    \
-    {                                                                    \
-        OdeFwdInline<4, 0, TERR> ode{mc, 0, u2[0], u2[1]};                \
-        rk4_fwd(ode, X, ACC, TT, KK, sk);                                 \
-        OdeBwdInline<4, TERR, HostAcc> odeb{mc, 0, u2[0], u2[1], acc};    \
-        rk4_bwd_nn(odeb, sk, sc, LAM, YB, KB, XS, SB);                    \
-    }
-    switch (m->terr) {
-        case 0: HC_STEP(0) break;
-        case 1: HC_STEP(1) break;
-        case 2: HC_STEP(2) break;
-        default: HC_STEP(3) break;
-    }
-#undef HC_STEP
-    for (int c = 0; c < 13; c++) lam[c] = LAM[c];
-    memcpy(lam_out13, lam, sizeof(lam));
-    memcpy(gW104, acc.g, sizeof(acc.g));
-}
 // SoA batch rollout, same buffers as the kernels
 void hc_rollout(const hc_model* m, int N, int T, int substeps, const double* x0, const double* ctrl, double* x_list, double* x_final) {
     ModelConst mc; mk(m, mc);
@@ -173,7 +147,7 @@ void hc_rollout(const hc_model* m, int N, int T, int substeps, const double* x0,
 }
 void hc_rollout_grad(const hc_model* m, int N, int T, int substeps, const double* x0, const double* ctrl, const double* gt, double* loss, double* gps104xN) {
     ModelConst mc; mk(m, mc);
-    std::vector<double> ckpt(((size_t)(T - 1) * substeps * 4 * kCkRows + 13) * N);
+    std::vector<double> ckpt(((size_t)(T - 1) * substeps * 4 + 1) * kCkRows * N);
     RolloutArgs a; memset(&a, 0, sizeof(a));
     a.N = N; a.Nc = N; a.T = T; a.substeps = substeps; a.x0 = x0; a.ctrl = ctrl; a.ckpt = ckpt.data(); a.gt = gt;
     for (int n = 0; n < N; n++) {

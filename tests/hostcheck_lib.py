@@ -100,13 +100,6 @@ def ode_vjp(m, X13, u, Xdb):
     return xb, g
 
 
-def rk4_vjp(m, X13, u, lam):
-    X13, u, lam = _f64(X13), _f64(u), _f64(lam)
-    out, g = np.zeros(13), np.zeros(104)
-    lib().hc_rk4_vjp(C.byref(m), _p(X13), _p(u), _p(lam), _p(out), _p(g))
-    return out, g
-
-
 def rollout(m, x0, ctrl, T, substeps=10, want_list=True):
     x0, ctrl = _f64(x0), _f64(ctrl)
     N = x0.shape[1]
