@@ -4,7 +4,7 @@
 // (/root/reference/src/Trainer.cpp:607-657).  Per RK4 step it reloads the four stage records the forward
 // sweep stored (coalesced, 448 B per vehicle-step), recomputes each stage's tire-network activations in
 // registers and immediately back-propagates through them.  dL/dW is accumulated per lane in a private
-// shared-memory column ([104][kBwdBlock] doubles next to 80 scratch rows for the loop-carried adjoints and the
+// shared-memory column ([104][kBwdBlock] doubles next to 100 scratch rows for the loop-carried adjoints and the
 // double-buffered checkpoint records that cp.async prefetches one stage ahead,
 // conflict-free: consecutive lanes -> consecutive banks), summed over the lanes of a vehicle at the end and
 // written as the per-sample gradient gps[104][N].
@@ -26,9 +26,11 @@ __global__ void __launch_bounds__(kBwdBlock) rollout_bwd_kernel(const __grid_con
 #pragma unroll 8
     for (int k = 0; k < kNumLive; k++) G[k] = 0.0;
     double loss;
-    auto mk_odeb = [lane0](double ul, double ur) { return OdeBwdCall<TERR, kBwdBlock>{lane0, 52, 26, 39, kBwdSlotG, ul, ur, 66}; };
+    auto mk_odeb = [lane0](double ul, double ur) { return OdeBwdCall<TERR, kBwdBlock>{lane0, 52, 26, 39, kBwdSlotG, ul, ur, 66, 80}; };
     const long nrec = (long)(a.T - 1) * a.substeps * 4;
-    CkptStreamAsync<kBwdBlock> st{a.ckpt + (size_t)nrec * kCkRows * a.Nc + n, (size_t)a.Nc, nrec, 52, 66, 0};
+    // the stream starts at the final-state record; its (non-existent) activation record is one past the last stage
+    CkptStreamAsync<kBwdBlock> st{a.ckpt + (size_t)nrec * kCkRows * a.Nc + n, (size_t)a.Nc, nrec, 52, 66, 0,
+                                  a.act + ((size_t)nrec * 4 * a.Nc + (size_t)4 * n + lane0) * kActLen, 80};
     st.init();
     rollout_bwd_body(a, n, loss, scratch_col<kBwdBlock>(0), st, mk_odeb);
     const bool writer = valid && lane0 == 0;

@@ -41,7 +41,7 @@ struct avs_ctx {
     double* d_sq = nullptr;      // [416] RMSProp state
     bool params_dirty_on_device = false;
     DevBuf grid_h, grid_s, ztab;
-    DevBuf ckpt, gps, loss, reduced, flags, settle;
+    DevBuf ckpt, act, gps, loss, reduced, flags, settle;
     DevBuf in_x0, in_ctrl, in_gt, out_list, out_final, io_a, io_b, io_c;
     long long launches = 0;
     std::string err;
@@ -151,7 +151,7 @@ void avs_destroy(avs_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = {&ctx->grid_h, &ctx->grid_s, &ctx->ztab, &ctx->ckpt, &ctx->gps, &ctx->loss, &ctx->reduced, &ctx->flags, &ctx->settle,
+    DevBuf* bufs[] = {&ctx->grid_h, &ctx->grid_s, &ctx->ztab, &ctx->ckpt, &ctx->act, &ctx->gps, &ctx->loss, &ctx->reduced, &ctx->flags, &ctx->settle,
                       &ctx->in_x0, &ctx->in_ctrl, &ctx->in_gt, &ctx->out_list, &ctx->out_final, &ctx->io_a, &ctx->io_b, &ctx->io_c};
     for (DevBuf* b : bufs) b->release();
     if (ctx->d_params) cudaFree(ctx->d_params);
@@ -324,26 +324,29 @@ int avs_rollout_grad_dev(avs_ctx* ctx, int N, int T, int substeps, const double*
     const size_t n = (size_t)N;
     if (!d_loss) { CK(ctx->loss.reserve(n * 8)); d_loss = ctx->loss.as<double>(); }
     if (!d_grad_live) { CK(ctx->gps.reserve((size_t)kNumLive * n * 8)); d_grad_live = ctx->gps.as<double>(); }
-    // checkpoint buffer: (S*4 + 1) records of 14 doubles per vehicle; process the batch in chunks if it does not fit the budget
-    const size_t per_vehicle = ((size_t)(T - 1) * substeps * 4 + 1) * kCkRows * 8;
+    // reverse-sweep buffers: (S*4 + 1) state records of 14 doubles + S*4 x 4 wheels activation records of 20 doubles per vehicle; process the batch in chunks if it does not fit the budget
+    const size_t per_vehicle_ck = ((size_t)(T - 1) * substeps * 4 + 1) * kCkRows * 8;
+    const size_t per_vehicle_act = (size_t)(T - 1) * substeps * 4 * kActLen * 4 * 8;
+    const size_t per_vehicle = per_vehicle_ck + per_vehicle_act;
     size_t budget = ctx->ckpt_budget;
     if (budget == 0) {
         size_t free_b = 0, total_b = 0;
         CK(cudaMemGetInfo(&free_b, &total_b));
-        budget = (size_t)((double)(free_b + ctx->ckpt.cap) * 0.6);
+        budget = (size_t)((double)(free_b + ctx->ckpt.cap + ctx->act.cap) * 0.6);
     }
     size_t chunk = budget / per_vehicle;
     if (chunk >= n) chunk = n;
     else chunk = (chunk / 256) * 256;  // whole CTAs
     if (chunk == 0) return fail(ctx, AVS_E_NOMEM, "avs_rollout_grad: checkpoint budget %zu B < one 256-vehicle chunk (%zu B)", budget, per_vehicle * 256);
-    CK(ctx->ckpt.reserve(chunk * per_vehicle));
+    CK(ctx->ckpt.reserve(chunk * per_vehicle_ck));
+    CK(ctx->act.reserve(chunk * per_vehicle_act));
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     for (size_t begin = 0; begin < n; begin += chunk) {
         const size_t cnt = (n - begin < chunk) ? (n - begin) : chunk;
         RolloutArgs a;
         memset(&a, 0, sizeof(a));
         a.N = N; a.Nc = (int)cnt; a.T = T; a.substeps = substeps;
-        a.x0 = d_x0 + begin; a.ctrl = d_ctrl + begin; a.gt = d_gt + begin; a.ckpt = ctx->ckpt.as<double>();
+        a.x0 = d_x0 + begin; a.ctrl = d_ctrl + begin; a.gt = d_gt + begin; a.ckpt = ctx->ckpt.as<double>(); a.act = ctx->act.as<double>();
         a.loss = d_loss + begin; a.gps = d_grad_live + begin;
         CK(launch_rollout_fwd(AVS_TIRE_NN, ctx->terr, true, ctx->mc, a, ctx->stream));
         if (begin == 0 && cnt == n) CK(cudaEventRecord(ctx->ev[1], ctx->stream));

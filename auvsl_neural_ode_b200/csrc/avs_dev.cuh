@@ -21,21 +21,25 @@ template <int BLOCK> __device__ __forceinline__ Scratch<BLOCK> scratch_col(int s
     return Scratch<BLOCK>{g_smem + slot * BLOCK + threadIdx.x};
 }
 
-// K = f(T):  T, K = scratch slots (13 columns each)
-template <int TIRE, int TERR, int BLOCK>
-__device__ __noinline__ void ode_fwd_call(int lane0, int slotT, int slotK, double ul, double ur) {
+// K = f(T):  T, K = scratch slots (13 columns each); act (STORE_ACT) = this lane's activation record of the stage
+template <int TIRE, int TERR, int BLOCK, bool STORE_ACT>
+__device__ __noinline__ void ode_fwd_call(int lane0, int slotT, int slotK, double ul, double ur, double* act) {
     const Scratch<BLOCK> T = scratch_col<BLOCK>(slotT), K = scratch_col<BLOCK>(slotK);
     double X[13], Xd[13];
 #pragma unroll
     for (int c = 0; c < 13; c++) X[c] = T[c];
-    ode_fwd<1, TIRE, TERR>(c_mc, lane0, X, ul, ur, Xd);
+    ode_fwd<1, TIRE, TERR, STORE_ACT>(c_mc, lane0, X, ul, ur, Xd, nullptr, ActOutPtr{act});
 #pragma unroll
     for (int c = 0; c < 13; c++) K[c] = Xd[c];
 }
-template <int TIRE, int TERR, int BLOCK> struct OdeFwdCall {
+template <int TIRE, int TERR, int BLOCK, bool STORE_ACT> struct OdeFwdCall {
     int lane0, slotT, slotK;
     double ul, ur;
-    __device__ __forceinline__ void operator()(Scratch<BLOCK>, Scratch<BLOCK>) const { ode_fwd_call<TIRE, TERR, BLOCK>(lane0, slotT, slotK, ul, ur); }
+    double* act_step;         // this lane's record of stage 0 of the current RK4 step
+    size_t act_stage_stride;  // doubles between consecutive stages
+    __device__ __forceinline__ void operator()(Scratch<BLOCK>, Scratch<BLOCK>, int s) const {
+        ode_fwd_call<TIRE, TERR, BLOCK, STORE_ACT>(lane0, slotT, slotK, ul, ur, STORE_ACT ? act_step + (size_t)s * act_stage_stride : nullptr);
+    }
 };
 
 // gradient accumulators: slot `slotG` + k, one private shared-memory column per lane
@@ -44,16 +48,38 @@ template <int BLOCK> struct SmemAcc {
     __device__ __forceinline__ void fma(int k, double a, double b) { col[k * BLOCK] = ::fma(a, b, col[k * BLOCK]); }
 };
 
+// activation record staged in shared memory as ten 16-byte pairs: pair i of this lane at base[i * BLOCK * 2]
+template <int BLOCK> struct ActInSmem {
+    const double* base;
+    __device__ __forceinline__ void load2(int i, double& a, double& b) const {
+        const double2 v = *reinterpret_cast<const double2*>(base + (size_t)i * BLOCK * 2);
+        a = v.x; b = v.y;
+    }
+    __device__ __forceinline__ ActInSmem wheel(int) const { return *this; }
+};
+template <int BLOCK> __device__ __forceinline__ void act_prefetch(int slotACT, const double* src) {
+#pragma unroll
+    for (int i = 0; i < kActLen / 2; i++) {
+        const unsigned saddr = (unsigned)__cvta_generic_to_shared(g_smem + (size_t)slotACT * BLOCK + ((size_t)i * BLOCK + threadIdx.x) * 2);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(src + 2 * i) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
 // SB = (df/dX)^T KB at XS, dL/dW += ...
 template <int TERR, int BLOCK>
-__device__ __noinline__ void ode_bwd_call(int lane0, int slotXS, int slotKB, int slotSB, int slotG, double ul, double ur) {
+__device__ __noinline__ void ode_bwd_call(int lane0, int slotXS, int slotKB, int slotSB, int slotG, int slotACT, double ul, double ur,
+                                          const double* act_next) {
     // (slotXS is dynamic: the record buffers alternate)
     const Scratch<BLOCK> XS = scratch_col<BLOCK>(slotXS), KB = scratch_col<BLOCK>(slotKB), SB = scratch_col<BLOCK>(slotSB);
     SmemAcc<BLOCK> acc{g_smem + slotG * BLOCK + threadIdx.x};
     double X[13], Xb[13];
 #pragma unroll
     for (int c = 0; c < 13; c++) X[c] = XS[c];
-    ode_bwd_nn<1, TERR>(c_mc, lane0, X, ul, ur, KB, Xb, acc);
+    ode_bwd_nn<1, TERR>(c_mc, lane0, X, ul, ur, KB, Xb, acc, ActInSmem<BLOCK>{g_smem + (size_t)slotACT * BLOCK + (size_t)threadIdx.x * 2});
+    // this stage's activation record is in registers now: refill the shared-memory slots with the previous
+    // stage's record (HBM -> smem, asynchronous; waited for by the stream's next advance())
+    if (act_next) act_prefetch<BLOCK>(slotACT, act_next);
 #pragma unroll
     for (int c = 0; c < 13; c++) SB[c] = Xb[c];
 }
@@ -61,9 +87,10 @@ template <int TERR, int BLOCK> struct OdeBwdCall {
     int lane0, slotXS, slotKB, slotSB, slotG;
     double ul, ur;
     int slotXB;  // second record buffer
-    __device__ __forceinline__ void operator()(Scratch<BLOCK> XS, Scratch<BLOCK>, Scratch<BLOCK>) const {
+    int slotACT;
+    __device__ __forceinline__ void operator()(Scratch<BLOCK> XS, Scratch<BLOCK>, Scratch<BLOCK>, const double* act_next) const {
         const bool isA = XS.p == scratch_col<BLOCK>(slotXS).p;
-        ode_bwd_call<TERR, BLOCK>(lane0, isA ? slotXS : slotXB, slotKB, slotSB, slotG, ul, ur);
+        ode_bwd_call<TERR, BLOCK>(lane0, isA ? slotXS : slotXB, slotKB, slotSB, slotG, slotACT, ul, ur, act_next);
     }
 };
 
@@ -75,6 +102,10 @@ template <int BLOCK> struct CkptStreamAsync {
     size_t stride;
     long remaining;      // records before the current one
     int slotA, slotB, parity;
+    const double* actp;  // this lane's activation record (HBM) of the current stage
+    int slotACT;
+    // token handed to the adjoint call: HBM address of the activation record it should prefetch next
+    __device__ __forceinline__ const double* act() const { return remaining > 0 ? actp - (size_t)kActLen * 4 * stride : nullptr; }
     __device__ __forceinline__ Scratch<BLOCK> cur() const { return scratch_col<BLOCK>(parity ? slotB : slotA); }
     __device__ __forceinline__ void prefetch_prev() {
         if (remaining <= 0) return;
@@ -92,11 +123,13 @@ template <int BLOCK> struct CkptStreamAsync {
 #pragma unroll
         for (int c = 0; c < kCkRows; c++) dst[c] = __ldg(rec + (size_t)c * stride);
         prefetch_prev();
+        if (remaining > 0) act_prefetch<BLOCK>(slotACT, actp - (size_t)kActLen * 4 * stride);  // first stage to be reversed
     }
     __device__ __forceinline__ void advance() {
         asm volatile("cp.async.wait_all;" ::: "memory");
         parity ^= 1;
         rec -= (size_t)kCkRows * stride;
+        actp -= (size_t)kActLen * 4 * stride;
         remaining--;
         prefetch_prev();
     }

@@ -11,7 +11,8 @@ __global__ void __launch_bounds__(kFwdBlock) rollout_fwd_kernel(const __grid_con
     const int lane0 = gid & 3;
     const bool valid = n < a.Nc;
     if (!valid) n = a.Nc - 1;  // tail lanes mirror the last vehicle so that group shuffles stay converged
-    auto mk_ode = [lane0](double ul, double ur) { return OdeFwdCall<TIRE, TERR, kFwdBlock>{lane0, 26, 39, ul, ur}; };
+    const size_t stage_stride = (size_t)4 * a.Nc * kActLen;
+    auto mk_ode = [lane0, stage_stride](double ul, double ur) { return OdeFwdCall<TIRE, TERR, kFwdBlock, STORE && TIRE == TIRE_NN>{lane0, 26, 39, ul, ur, nullptr, stage_stride}; };
     rollout_fwd_body<STORE>(a, n, lane0, valid, scratch_col<kFwdBlock>(0), mk_ode);
 }
 

@@ -37,7 +37,7 @@ __global__ void settle_kernel(double* __restrict__ state21) {
     const double x_init[13] = {0, 0, 0, 1, 0, 0, 0.16, 0, 0, 0, 0, 0, 0};
 #pragma unroll
     for (int c = 0; c < 13; c++) X[c] = x_init[c];
-    OdeFwdCall<TIRE, TERR_DYN, 32> ode{lane0, 26, 39, 0.0, 0.0};
+    OdeFwdCall<TIRE, TERR_DYN, 32, false> ode{lane0, 26, 39, 0.0, 0.0, nullptr, 0};
 #pragma unroll 1
     for (int it = 0; it < 1000; it++) {
         double q[4] = {X[0], X[1], X[2], X[3]}, R[9];

@@ -500,6 +500,43 @@ AVS_HD void quat_to_R_bwd(const double q[4], const double Rb[9], double qb[4]) {
     qb[3] += 2.0 * (z * a01 + y * a02 + x * a12);
 }
 
+// ---- activation record: what the reverse sweep needs from one tire-network evaluation ------------------
+// Stored by the forward sweep (one record per wheel per RK4 stage) so that the adjoint does not re-evaluate the
+// 16 tanh: kActLen = 20 contiguous doubles  h0[8] | h2[8] | dz = (z4 > 0 ? dz4/ds0 : 0) | pad | dalt/dx | dalt/dy,
+// written and read as ten 16-byte pairs (STG.128 / 16-byte cp.async).  The scaled inputs s1..s3 are cheaper to
+// recompute from the stage state than to store.
+constexpr int kActLen = 20;
+struct ActOutPtr {  // contiguous record in (global / host) memory, 16-byte aligned
+    double* p;
+    AVS_HD void store2(int i, double a, double b) const {
+#if defined(__CUDA_ARCH__)
+        *reinterpret_cast<double2*>(p + 2 * i) = make_double2(a, b);
+#else
+        p[2 * i] = a; p[2 * i + 1] = b;
+#endif
+    }
+    AVS_HD ActOutPtr wheel(int k) const { return ActOutPtr{p + (size_t)k * kActLen}; }
+};
+struct ActInPtr {
+    const double* p;
+    AVS_HD void load2(int i, double& a, double& b) const { a = p[2 * i]; b = p[2 * i + 1]; }
+    AVS_HD ActInPtr wheel(int k) const { return ActInPtr{p + (size_t)k * kActLen}; }
+};
+template <class AOut> AVS_HD void act_store(const NNAct& a, double dax, double day, const AOut& o) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) { o.store2(j, a.h0[2 * j], a.h0[2 * j + 1]); o.store2(4 + j, a.h2[2 * j], a.h2[2 * j + 1]); }
+    o.store2(8, a.z4 > 0.0 ? a.dz4 : 0.0, 0.0);
+    o.store2(9, dax, day);
+}
+template <class AIn> AVS_HD void act_load(NNAct& a, double& dax, double& day, const AIn& in) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) { in.load2(j, a.h0[2 * j], a.h0[2 * j + 1]); in.load2(4 + j, a.h2[2 * j], a.h2[2 * j + 1]); }
+    double pad;
+    in.load2(8, a.dz4, pad);
+    a.z4 = 1.0;  // the relu gate is already folded into dz
+    in.load2(9, dax, day);
+}
+
 // ------------------------------------------------------------------------------------------------
 // One wheel: contact geometry -> tire force -> ABA passes 1 and 2 -> contribution X_i^T pa_i to the
 // base bias force.  (HybridDynamics.cpp:214-253, 321-417; generated/forward_dynamics.cpp:56-153)
@@ -564,6 +601,18 @@ AVS_HD void wheel_aba_fwd(double tx, double ty, const double X[13], double qd, c
     C[1] = (kTz * fb0 - tx * fb2);
     C[2] = -pa1 + (tx * fb1 - ty * fb0);
     C[3] = fb0; C[4] = fb1; C[5] = fb2;
+}
+
+// the part of wheel_aba_fwd the adjoint needs (wheel-frame velocities and I_w w)
+AVS_HD void wheel_aba_act(double tx, double ty, const double X[13], double qd, WheelAct& a) {
+    const double* w = X + 7; const double* v = X + 10;
+    a.w0 = w[0]; a.w1 = -w[2]; a.w2 = w[1] + qd;
+    a.u0 = v[0] + (w[1] * kTz - w[2] * ty);
+    a.u1 = -(v[2] + (w[0] * ty - w[1] * tx));
+    a.u2 = v[1] + (w[2] * tx - w[0] * kTz);
+    a.n0 = kIwxx * a.w0;
+    a.n1 = kIwyy * a.w1 - kIwyz * a.w2;
+    a.n2 = kIwzz * a.w2 - kIwyz * a.w1;
 }
 
 // adjoint of wheel_aba_fwd: Cb[6] -> Fb[3] (tire force adjoint) and += into wb[3], vb[3]
@@ -746,8 +795,11 @@ AVS_HD void wheel_sign(int i, double& tx, double& ty) {
 //   ws (optional) = the four joint-velocity state entries X[17..20]: the tire models read THOSE as the wheel
 //   speed (HybridDynamics.cpp:384, BekkerDynamics.cpp:68) while the ABA uses the control; inside integrate()
 //   both are equal (VehicleSystem.cpp:132-133), so rollouts pass nullptr.
-template <int WPT, int TIRE, int TERR>
-AVS_HD void ode_fwd(const ModelConst& mc, int lane0, const double X[13], double ul, double ur, double Xd[13], const double* ws = nullptr) {
+//   act_out (STORE_ACT, NN only) = activation record of this thread's first wheel; the records of its WPT
+//   wheels are consecutive (kActLen doubles each)
+template <int WPT, int TIRE, int TERR, bool STORE_ACT = false>
+AVS_HD void ode_fwd(const ModelConst& mc, int lane0, const double X[13], double ul, double ur, double Xd[13], const double* ws = nullptr,
+                    ActOutPtr act_out = ActOutPtr{nullptr}) {
     double R[9];
     quat_to_R(X, R);
     double S[6] = {0, 0, 0, 0, 0, 0};
@@ -762,8 +814,9 @@ AVS_HD void ode_fwd(const ModelConst& mc, int lane0, const double X[13], double 
         wheel_contact<TERR>(mc, tx, ty, R, X, sink, cv, dax, day, cp);
         const double wsp = ws ? ws[i] : qd;
         if (TIRE == TIRE_NN) {
-            tire_nn_fwd(mc, cv[0], cv[1], wsp, sink, F, act.nn);
+            tire_nn_fwd<STORE_ACT>(mc, cv[0], cv[1], wsp, sink, F, act.nn);
             F[2] = fma(kNNDamp, cv[2], F[2]);
+            if (STORE_ACT) act_store(act.nn, dax, day, act_out.wheel(k));
         } else {
             bekker_tire_fwd<TERR>(mc, cv[0], cv[1], wsp, sink, cp, F);
             F[2] = fma(kBekkerDamp, cv[2], F[2]);
@@ -778,13 +831,13 @@ AVS_HD void ode_fwd(const ModelConst& mc, int lane0, const double X[13], double 
 }
 
 // Adjoint of the ODE at stage input X:  Xb = (df/dX)^T Xdb (overwritten) ; weight gradients into acc.
-// Xdb is indexable (scratch column).  The wheel forward is recomputed here so that its activations never
-// leave registers; the base-link part that needs X and R again runs after the wheel part so that nothing
-// but Sb[6] has to stay live across the tire network.
-template <int WPT, int TERR, class XD, class Acc>
-AVS_HD void ode_bwd_nn(const ModelConst& mc, int lane0, const double X[13], double ul, double ur, const XD& Xdb, double Xb[13], Acc& acc) {
-    double R[9];
-    quat_to_R(X, R);
+// Xdb is indexable (scratch column).  The tire-network activations and terrain gradients come from the records
+// the forward sweep stored, so neither the tanh nor the terrain lookup is
+// re-evaluated (act_in.wheel(k) = record of this thread's k-th wheel).  The base-link part that needs X and R again runs after the wheel part so that nothing but Sb[6]
+// has to stay live across the tire-network adjoint.
+template <int WPT, int TERR, class XD, class Acc, class AIn>
+AVS_HD void ode_bwd_nn(const ModelConst& mc, int lane0, const double X[13], double ul, double ur, const XD& Xdb, double Xb[13], Acc& acc,
+                       const AIn& act_in) {
     double Sb[6];
     base_bwd_S(mc, Xdb, Sb);
     // wheel-local adjoints, summed over the group: cp_bar (x) r  ->  Rb, pb ; wb ; vb
@@ -796,12 +849,16 @@ AVS_HD void ode_bwd_nn(const ModelConst& mc, int lane0, const double X[13], doub
         double tx, ty;
         wheel_sign(i, tx, ty);
         const double qd = (i & 1) ? ur : ul;
-        double sink, cv[3], dax, day, cp[3], F[3], C[6], Fb[3];
+        double dax, day, Fb[3];
         WheelAct act;
-        wheel_contact<TERR>(mc, tx, ty, R, X, sink, cv, dax, day, cp);
-        tire_nn_fwd<true>(mc, cv[0], cv[1], qd, sink, F, act.nn);
-        F[2] = fma(kNNDamp, cv[2], F[2]);
-        wheel_aba_fwd(tx, ty, X, qd, F, C, act);
+        act_load(act.nn, dax, day, act_in.wheel(k));
+        {   // scaled tire-network inputs from the stage state (TireNetwork.cpp:73-89; cv = v + w x r)
+            const double cvx = X[10] + (X[8] * kRz - X[9] * ty), cvy = X[11] + (X[9] * tx - X[7] * kRz);
+            act.nn.s1 = (qd * kTireRadius - cvx) * (1.0 / kInStd1);
+            act.nn.s2 = qd * (1.0 / kInStd2);
+            act.nn.s3 = cvy * (1.0 / kInStd3);
+        }
+        wheel_aba_act(tx, ty, X, qd, act);
         wheel_aba_bwd(tx, ty, qd, act, Sb, Fb, wb, vb);
         double cvb[3], sinkb;
         cvb[2] = kNNDamp * Fb[2];
@@ -823,7 +880,8 @@ AVS_HD void ode_bwd_nn(const ModelConst& mc, int lane0, const double X[13], doub
         gx[c] = Group<WPT>::sum(gx[c]); gy[c] = Group<WPT>::sum(gy[c]); gs[c] = Group<WPT>::sum(gs[c]);
         wb[c] = Group<WPT>::sum(wb[c]); vb[c] = Group<WPT>::sum(vb[c]);
     }
-    double Rb[9];
+    double R[9], Rb[9];
+    quat_to_R(X, R);
     base_bwd_rest(R, X, Xdb, Sb, Xb, Rb);
     // cp = R r + p with r = (sx*kTx, sy*kTy, kRz)
 #pragma unroll
@@ -863,7 +921,7 @@ struct NullSink {
 };
 
 // One RK4 step.  All loop-carried state lives in per-thread scratch columns (X in/out; ACC, T, K scratch,
-// 13 slots each); `ode(T, K)` evaluates K = f(T).  On the device `ode` is a call to a NON-inlined function:
+// 13 slots each); `ode(T, K, s)` evaluates K = f(T) for stage s.  On the device `ode` is a call to a NON-inlined function:
 // ptxas schedules the body of a rolled loop for minimum register pressure and re-serialises independent
 // dependency chains, whereas a stand-alone function body keeps the interleaved (ILP) order it is written in.
 // The four stages run as a rolled loop; the stage weights of HybridDynamics.cpp:470-495 are selected by index.
@@ -876,7 +934,7 @@ AVS_HD void rk4_fwd(Ode& ode, St X, St ACC, St T, St K, Sink& sink) {
 #pragma unroll 1
     for (int s = 0; s < 4; s++) {
         sink.stage(s, T, inv);
-        ode(T, K);
+        ode(T, K, s);
         const double wgt = (s == 0 || s == 3) ? 1.0 : 2.0;   // k1 + 2 k2 + 2 k3 + k4
         const double cs = (s == 2) ? h : .5 * h;             // X + .5h k1, X + .5h k2, X + h k3
 #pragma unroll
@@ -896,7 +954,8 @@ AVS_HD void rk4_fwd(Ode& ode, St X, St ACC, St T, St K, Sink& sink) {
 // that produced that stage input; slot 13 of a stage-0 record holds the inverse norm of the PREVIOUS step's final
 // normalisation (so that the record that serves as "state after the step" also delivers that step's norm).
 // On entry st.cur() is the record after this step; st.advance() steps to the previous record (and prefetches the
-// one before it).  `odeb(XS, KB, SB)`: SB = (df/dX)^T KB at stage input XS (+ weight-gradient accumulation).
+// one before it).  `odeb(XS, KB, SB, act)`: SB = (df/dX)^T KB at stage input XS (+ weight-gradient accumulation), act = the
+// stage's activation records.
 // LAM (13, in/out) = adjoint of the step output on entry, adjoint of the step input on return.
 template <class OdeB, class Stream, class St>
 AVS_HD void rk4_bwd_nn(OdeB& odeb, Stream& st, St LAM, St YB, St KB, St SB) {
@@ -912,7 +971,7 @@ AVS_HD void rk4_bwd_nn(OdeB& odeb, Stream& st, St LAM, St YB, St KB, St SB) {
     for (int s = 3; s >= 0; s--) {
         st.advance();
         const St XS = st.cur();
-        odeb(XS, KB, SB);
+        odeb(XS, KB, SB, st.act());
         if (s > 0) {
             const double inv_s = XS[13];
             renorm_bwd(XS, inv_s, SB);  // stage input s = N(X + c_s k_s)
@@ -928,24 +987,26 @@ AVS_HD void rk4_bwd_nn(OdeB& odeb, Stream& st, St LAM, St YB, St KB, St SB) {
 }
 
 // inline ODE functors (host harness; the device kernels use non-inlined calls, see avs_dev.cuh)
-template <int WPT, int TIRE, int TERR> struct OdeFwdInline {
+template <int WPT, int TIRE, int TERR, bool STORE_ACT> struct OdeFwdInline {
     const ModelConst& mc; int lane0; double ul, ur;
-    template <class St> AVS_HD void operator()(St T, St K) const {
+    double* act_step;  // activation records of the current RK4 step (this thread's first wheel, stage 0)
+    size_t act_stage_stride;  // doubles between the records of consecutive stages
+    template <class St> AVS_HD void operator()(St T, St K, int s) const {
         double X[13], Xd[13];
 #pragma unroll
         for (int c = 0; c < 13; c++) X[c] = T[c];
-        ode_fwd<WPT, TIRE, TERR>(mc, lane0, X, ul, ur, Xd);
+        ode_fwd<WPT, TIRE, TERR, STORE_ACT>(mc, lane0, X, ul, ur, Xd, nullptr, ActOutPtr{STORE_ACT ? act_step + (size_t)s * act_stage_stride : nullptr});
 #pragma unroll
         for (int c = 0; c < 13; c++) K[c] = Xd[c];
     }
 };
 template <int WPT, int TERR, class Acc> struct OdeBwdInline {
     const ModelConst& mc; int lane0; double ul, ur; Acc& acc;
-    template <class St> AVS_HD void operator()(St XS, St KB, St SB) const {
+    template <class St> AVS_HD void operator()(St XS, St KB, St SB, const double* act) const {
         double X[13], Xb[13];
 #pragma unroll
         for (int c = 0; c < 13; c++) X[c] = XS[c];
-        ode_bwd_nn<WPT, TERR>(mc, lane0, X, ul, ur, KB, Xb, acc);
+        ode_bwd_nn<WPT, TERR>(mc, lane0, X, ul, ur, KB, Xb, acc, ActInPtr{act});
 #pragma unroll
         for (int c = 0; c < 13; c++) SB[c] = Xb[c];
     }

@@ -14,6 +14,8 @@
 //   ckpt    [S*4+1][14][Nc]  one record per RK4 stage (S = (T-1)*substeps steps) + one for the final state:
 //                            13 state entries + the inverse quaternion norm the reverse sweep needs with it.
 //                            This stream replaces the tape (448 B per vehicle-step)
+//   act     [S*4][4*Nc][20]  per-wheel tire-network activation records of every stage (2560 B per vehicle-step):
+//                            the reverse sweep reads them instead of re-evaluating tanh / terrain
 //   gt      [T][3][N]        (yaw, x, y) ground truth rows
 //   loss    [N], gps [104][N] per-sample loss and gradient w.r.t. the live tire-network weights
 #pragma once
@@ -30,6 +32,7 @@ struct RolloutArgs {
     double* x_list;
     double* x_final;
     double* ckpt;
+    double* act;  // [S*4][4*Nc][kActLen] tire-network activation records (column 4n + wheel), STORE only
     const double* gt;
     double* loss;
     double* gps;
@@ -69,12 +72,14 @@ template <class St> struct CkptStreamSimple {
     const double* rec;  // current record in HBM
     size_t stride;
     St buf;             // 14-slot scratch column
+    const double* actp; // activation records of the current record's stage (lane-offset applied)
+    AVS_HD const double* act() const { return actp; }
     AVS_HD void load() {
 #pragma unroll
         for (int c = 0; c < kCkRows; c++) buf[c] = ld(rec + (size_t)c * stride);
     }
     AVS_HD St cur() const { return buf; }
-    AVS_HD void advance() { rec -= (size_t)kCkRows * stride; load(); }
+    AVS_HD void advance() { rec -= (size_t)kCkRows * stride; actp -= (size_t)kActLen * 4 * stride; load(); }
 };
 
 // live-state index -> reference 21-state index
@@ -105,6 +110,7 @@ AVS_HD void rollout_fwd_body(const RolloutArgs& a, int n, int lane0, bool valid,
         auto ode = mk_ode(ul, ur);
 #pragma unroll 1
         for (int s = 0; s < a.substeps; s++) {
+            if (STORE) ode.act_step = a.act + (((size_t)((size_t)(i - 1) * a.substeps + s) * 4) * (4 * NK) + (size_t)4 * n + lane0) * kActLen;
             if (STORE) {
                 CkptSink sink{a.ckpt + ((size_t)((size_t)(i - 1) * a.substeps + s) * 4) * kCkRows * NK + n, NK, writer};
                 rk4_fwd(ode, X, ACC, TT, KK, sink);
@@ -145,7 +151,7 @@ AVS_HD void rollout_fwd_body(const RolloutArgs& a, int n, int lane0, bool valid,
     }
 }
 
-constexpr int kBwdScratch = 80;  // LAM[13] | YB[13] | KB[13] | SB[13] | record buffer A[14] | record buffer B[14]
+constexpr int kBwdScratch = 100;  // LAM[13] | YB[13] | KB[13] | SB[13] | record buffer A[14] | record buffer B[14] | activation record[20]
 
 // Reverse sweep over the checkpoints written by rollout_fwd_body<.., STORE=true>.
 //   L = (sum_{i=1}^{T-1} l_i) / T / traj_len   (Trainer.cpp:612-649)

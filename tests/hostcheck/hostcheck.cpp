@@ -52,7 +52,7 @@ template <int TIRE, int TERR> static void rk413(const ModelConst& mc, const doub
     double sc[52];
     Scratch<1> X{sc}, ACC{sc + 13}, TT{sc + 26}, KK{sc + 39};
     for (int c = 0; c < 13; c++) X[c] = X13[c];
-    OdeFwdInline<4, TIRE, TERR> ode{mc, 0, u[0], u[1]};
+    OdeFwdInline<4, TIRE, TERR, false> ode{mc, 0, u[0], u[1], nullptr, 0};
     rk4_fwd(ode, X, ACC, TT, KK, sink);
     for (int c = 0; c < 13; c++) Xn13[c] = X[c];
     if (stages) memcpy(stages, sink.St, sizeof(sink.St));
@@ -71,15 +71,20 @@ template <int TIRE, int TERR> static void rk413(const ModelConst& mc, const doub
 
 template <int TIRE, int TERR> static void fwd_body(const ModelConst& mc, const RolloutArgs& a, int n, bool store) {
     double sc[kFwdScratch];
-    auto mk = [&mc](double ul, double ur) { return OdeFwdInline<4, TIRE, TERR>{mc, 0, ul, ur}; };
-    if (store) rollout_fwd_body<true>(a, n, 0, true, Scratch<1>{sc}, mk);
-    else rollout_fwd_body<false>(a, n, 0, true, Scratch<1>{sc}, mk);
+    const size_t stage_stride = (size_t)4 * a.Nc * kActLen;
+    if (store) {
+        auto mk = [&mc, stage_stride](double ul, double ur) { return OdeFwdInline<4, TIRE, TERR, TIRE == 0>{mc, 0, ul, ur, nullptr, stage_stride}; };
+        rollout_fwd_body<true>(a, n, 0, true, Scratch<1>{sc}, mk);
+    } else {
+        auto mk = [&mc](double ul, double ur) { return OdeFwdInline<4, TIRE, TERR, false>{mc, 0, ul, ur, nullptr, 0}; };
+        rollout_fwd_body<false>(a, n, 0, true, Scratch<1>{sc}, mk);
+    }
 }
 template <int TERR> static void bwd_body(const ModelConst& mc, const RolloutArgs& a, int n, HostAcc& acc, double& loss) {
     double sc[kBwdScratch];
     auto mk = [&mc, &acc](double ul, double ur) { return OdeBwdInline<4, TERR, HostAcc>{mc, 0, ul, ur, acc}; };
     const size_t nrec = (size_t)(a.T - 1) * a.substeps * 4;
-    CkptStreamSimple<Scratch<1>> st{a.ckpt + nrec * kCkRows * a.Nc + n, (size_t)a.Nc, Scratch<1>{sc + 52}};
+    CkptStreamSimple<Scratch<1>> st{a.ckpt + nrec * kCkRows * a.Nc + n, (size_t)a.Nc, Scratch<1>{sc + 52}, a.act + (nrec * 4 * a.Nc + (size_t)4 * n) * kActLen};
     st.load();
     rollout_bwd_body(a, n, loss, Scratch<1>{sc}, st, mk);
 }
@@ -127,14 +132,14 @@ void hc_rk4(const hc_model* m, const double* X13, const double* u2, double* Xn13
 void hc_ode_vjp(const hc_model* m, const double* X13, const double* u2, const double* Xdb13, double* Xb13, double* gW104) {
     ModelConst mc; mk(m, mc);
     HostAcc acc;
-    double kb[13];
+    double kb[13], Xd[13], actrec[kActLen * 4];
     memcpy(kb, Xdb13, sizeof(kb));
     Scratch<1> KB{kb};
-    switch (m->terr) {
-        case 0: ode_bwd_nn<4, 0>(mc, 0, X13, u2[0], u2[1], KB, Xb13, acc); break;
-        case 1: ode_bwd_nn<4, 1>(mc, 0, X13, u2[0], u2[1], KB, Xb13, acc); break;
-        case 2: ode_bwd_nn<4, 2>(mc, 0, X13, u2[0], u2[1], KB, Xb13, acc); break;
-        default: ode_bwd_nn<4, 3>(mc, 0, X13, u2[0], u2[1], KB, Xb13, acc); break;
+    switch (m->terr) {  // forward with activation store (four consecutive 20-double records), then the adjoint
+        case 0: ode_fwd<4, 0, 0, true>(mc, 0, X13, u2[0], u2[1], Xd, nullptr, ActOutPtr{actrec}); ode_bwd_nn<4, 0>(mc, 0, X13, u2[0], u2[1], KB, Xb13, acc, ActInPtr{actrec}); break;
+        case 1: ode_fwd<4, 0, 1, true>(mc, 0, X13, u2[0], u2[1], Xd, nullptr, ActOutPtr{actrec}); ode_bwd_nn<4, 1>(mc, 0, X13, u2[0], u2[1], KB, Xb13, acc, ActInPtr{actrec}); break;
+        case 2: ode_fwd<4, 0, 2, true>(mc, 0, X13, u2[0], u2[1], Xd, nullptr, ActOutPtr{actrec}); ode_bwd_nn<4, 2>(mc, 0, X13, u2[0], u2[1], KB, Xb13, acc, ActInPtr{actrec}); break;
+        default: ode_fwd<4, 0, 3, true>(mc, 0, X13, u2[0], u2[1], Xd, nullptr, ActOutPtr{actrec}); ode_bwd_nn<4, 3>(mc, 0, X13, u2[0], u2[1], KB, Xb13, acc, ActInPtr{actrec}); break;
     }
     memcpy(gW104, acc.g, sizeof(acc.g));
 }
@@ -149,7 +154,8 @@ void hc_rollout_grad(const hc_model* m, int N, int T, int substeps, const double
     ModelConst mc; mk(m, mc);
     std::vector<double> ckpt(((size_t)(T - 1) * substeps * 4 + 1) * kCkRows * N);
     RolloutArgs a; memset(&a, 0, sizeof(a));
-    a.N = N; a.Nc = N; a.T = T; a.substeps = substeps; a.x0 = x0; a.ctrl = ctrl; a.ckpt = ckpt.data(); a.gt = gt;
+    std::vector<double> actbuf((size_t)(T - 1) * substeps * 4 * kActLen * 4 * N);
+    a.N = N; a.Nc = N; a.T = T; a.substeps = substeps; a.x0 = x0; a.ctrl = ctrl; a.ckpt = ckpt.data(); a.act = actbuf.data(); a.gt = gt;
     for (int n = 0; n < N; n++) {
         DISPATCH(fwd_body, 0, m->terr, mc, a, n, true);
         HostAcc acc;

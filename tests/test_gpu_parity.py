@@ -148,7 +148,7 @@ def test_checkpoint_chunking_is_transparent(nn):
     N, T = 600, 6
     x0, ctrl, gt = synth.make_batch(N, T, seed=77)
     loss_a, red_a, gps_a = nn.rollout_grad(x0, ctrl, gt, T)
-    per_vehicle = ((T - 1) * 10 * 4 + 1) * 14 * 8
+    per_vehicle = ((T - 1) * 10 * 4 + 1) * 14 * 8 + (T - 1) * 10 * 4 * 20 * 4 * 8  # state records + activation records
     nn.set_checkpoint_budget(per_vehicle * 256 + 64)  # forces 256-vehicle chunks: 256 + 256 + 88
     loss_b, red_b, gps_b = nn.rollout_grad(x0, ctrl, gt, T)
     nn.set_checkpoint_budget(0)
