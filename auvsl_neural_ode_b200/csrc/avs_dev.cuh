@@ -76,10 +76,10 @@ __device__ __noinline__ void ode_bwd_call(int lane0, int slotXS, int slotKB, int
     double X[13], Xb[13];
 #pragma unroll
     for (int c = 0; c < 13; c++) X[c] = XS[c];
-    ode_bwd_nn<1, TERR>(c_mc, lane0, X, ul, ur, KB, Xb, acc, ActInSmem<BLOCK>{g_smem + (size_t)slotACT * BLOCK + (size_t)threadIdx.x * 2});
-    // this stage's activation record is in registers now: refill the shared-memory slots with the previous
-    // stage's record (HBM -> smem, asynchronous; waited for by the stream's next advance())
-    if (act_next) act_prefetch<BLOCK>(slotACT, act_next);
+    // once this stage's activation record is in registers, refill the shared-memory slots with the previous stage's
+    // record (HBM -> smem, asynchronous; a whole stage of compute later the stream's next advance() waits for it)
+    auto refill = [slotACT, act_next]() { if (act_next) act_prefetch<BLOCK>(slotACT, act_next); };
+    ode_bwd_nn<1, TERR>(c_mc, lane0, X, ul, ur, KB, Xb, acc, ActInSmem<BLOCK>{g_smem + (size_t)slotACT * BLOCK + (size_t)threadIdx.x * 2}, refill);
 #pragma unroll
     for (int c = 0; c < 13; c++) SB[c] = Xb[c];
 }

@@ -835,9 +835,12 @@ AVS_HD void ode_fwd(const ModelConst& mc, int lane0, const double X[13], double 
 // the forward sweep stored, so neither the tanh nor the terrain lookup is
 // re-evaluated (act_in.wheel(k) = record of this thread's k-th wheel).  The base-link part that needs X and R again runs after the wheel part so that nothing but Sb[6]
 // has to stay live across the tire-network adjoint.
-template <int WPT, int TERR, class XD, class Acc, class AIn>
+struct NoHook { AVS_HD void operator()() const {} };
+// after_load() runs once the activation records have been read (the device uses it to start refilling the
+// shared-memory staging slots with the next record while this stage computes)
+template <int WPT, int TERR, class XD, class Acc, class AIn, class Hook = NoHook>
 AVS_HD void ode_bwd_nn(const ModelConst& mc, int lane0, const double X[13], double ul, double ur, const XD& Xdb, double Xb[13], Acc& acc,
-                       const AIn& act_in) {
+                       const AIn& act_in, const Hook& after_load = Hook()) {
     double Sb[6];
     base_bwd_S(mc, Xdb, Sb);
     // wheel-local adjoints, summed over the group: cp_bar (x) r  ->  Rb, pb ; wb ; vb
@@ -852,6 +855,7 @@ AVS_HD void ode_bwd_nn(const ModelConst& mc, int lane0, const double X[13], doub
         double dax, day, Fb[3];
         WheelAct act;
         act_load(act.nn, dax, day, act_in.wheel(k));
+        if (k == WPT - 1) after_load();
         {   // scaled tire-network inputs from the stage state (TireNetwork.cpp:73-89; cv = v + w x r)
             const double cvx = X[10] + (X[8] * kRz - X[9] * ty), cvy = X[11] + (X[9] * tx - X[7] * kRz);
             act.nn.s1 = (qd * kTireRadius - cvx) * (1.0 / kInStd1);
