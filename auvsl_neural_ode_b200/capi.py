@@ -22,7 +22,7 @@ EXPORTS = [
     "avs_set_nn_params", "avs_get_nn_params", "avs_set_bekker_params", "avs_get_bekker_params", "avs_set_terrain_analytic",
     "avs_set_terrain_grid", "avs_set_checkpoint_budget", "avs_whole_body_com", "avs_init_state_com", "avs_settle", "avs_ode",
     "avs_rollout", "avs_rollout_dev", "avs_rollout_grad", "avs_rollout_grad_dev", "avs_rmsprop_step_dev", "avs_rmsprop_step", "avs_reset_optimizer",
-    "avs_stream", "avs_set_stream", "avs_sync", "avs_kernel_launches", "avs_last_kernel_ms", "avs_measure_fp64_peak",
+    "avs_stream", "avs_set_stream", "avs_use_own_stream", "avs_sync", "avs_kernel_launches", "avs_last_kernel_ms", "avs_measure_fp64_peak",
 ]
 
 
@@ -66,6 +66,7 @@ def lib():
         L.avs_stream.argtypes = [vp]
         L.avs_stream.restype = vp
         L.avs_set_stream.argtypes = [vp, vp]
+        L.avs_use_own_stream.argtypes = [vp]
         L.avs_sync.argtypes = [vp]
         L.avs_kernel_launches.argtypes = [vp]
         L.avs_kernel_launches.restype = C.c_longlong
@@ -234,7 +235,11 @@ class Context:
         return lib().avs_stream(self._h)
 
     def set_stream(self, cuda_stream_handle):
+        """Enqueue on a caller-owned stream (0 / None = the legacy default stream)."""
         self._ck(lib().avs_set_stream(self._h, cuda_stream_handle or None))
+
+    def use_own_stream(self):
+        self._ck(lib().avs_use_own_stream(self._h))
 
     def sync(self):
         self._ck(lib().avs_sync(self._h))

@@ -420,7 +420,14 @@ int avs_set_stream(avs_ctx* ctx, void* stream) {
     if (!ctx) return AVS_E_ARG;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
-    ctx->stream = stream ? (cudaStream_t)stream : ctx->own_stream;
+    ctx->stream = (cudaStream_t)stream;  // NULL is a valid handle: the legacy default stream
+    return AVS_OK;
+}
+int avs_use_own_stream(avs_ctx* ctx) {
+    if (!ctx) return AVS_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = ctx->own_stream;
     return AVS_OK;
 }
 int avs_sync(avs_ctx* ctx) {

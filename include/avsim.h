@@ -127,8 +127,9 @@ int avs_reset_optimizer(avs_ctx* ctx);
 
 /* ---- stream / bookkeeping */
 void* avs_stream(avs_ctx* ctx);                 /* cudaStream_t the *_dev calls are enqueued on */
-/* enqueue on a caller-owned cudaStream_t instead (NULL = back to the context's own stream) */
+/* enqueue on a caller-owned cudaStream_t instead (NULL = the legacy default stream); avs_use_own_stream reverts */
 int avs_set_stream(avs_ctx* ctx, void* stream);
+int avs_use_own_stream(avs_ctx* ctx);
 int avs_sync(avs_ctx* ctx);
 long long avs_kernel_launches(const avs_ctx* ctx); /* kernels launched by this context so far */
 /* average duration in ms of the most recent rollout kernels (CUDA events on the ctx stream; valid after avs_sync) */

@@ -236,6 +236,35 @@ def test_full_size_properties(nn):
     assert rel_state_err(xf[:, idx], xf_o) < STATE_RTOL
 
 
+def test_external_stream_orders_with_torch(nn):
+    """avs_set_stream(0) = the legacy default stream: torch events on it must bracket the context's kernels
+    (regression: a NULL handle used to fall back to the context's private stream, so event timing and NCCL
+    ordering on torch's stream silently missed the work)."""
+    import torch
+    N, T = 512, 40
+    x0, ctrl, gt = synth.make_batch(N, T, seed=3)
+    dev = torch.device("cuda:0")
+    d = [torch.from_numpy(a).to(dev) for a in (x0, ctrl, gt)]
+    loss = torch.zeros(N, dtype=torch.float64, device=dev)
+    red = torch.zeros(418, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream()
+    nn.set_stream(stream.cuda_stream)
+    try:
+        for _ in range(2):
+            nn.rollout_grad_dev(N, T, 10, d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), loss.data_ptr(), red.data_ptr())
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        nn.rollout_grad_dev(N, T, 10, d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), loss.data_ptr(), red.data_ptr())
+        e1.record(stream)
+        total = red.sum().item()  # implicit sync on torch's stream only: must already see the kernel's result
+        f, b = nn.last_kernel_ms()
+        assert e0.elapsed_time(e1) >= 0.98 * (f + b) > 0
+        assert np.isfinite(total) and red[417].item() == N
+    finally:
+        nn.use_own_stream()
+
+
 def test_argument_errors(nn):
     with pytest.raises(capi.AvsError):
         nn.set_terrain(9)
