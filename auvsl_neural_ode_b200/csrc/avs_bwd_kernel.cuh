@@ -41,13 +41,13 @@ __global__ void __launch_bounds__(kBwdBlock) rollout_bwd_kernel(const __grid_con
     if (writer) a.loss[n] = loss;
 }
 
-template <int TERR> static cudaError_t launch_bwd_t(const ModelConst& mc, const RolloutArgs& a, cudaStream_t s) {
+template <int TERR> static cudaError_t launch_bwd_t(const ModelConst& mc, const double* d_live, const RolloutArgs& a, cudaStream_t s) {
     const long long threads = (long long)a.Nc * 4;
     const int grid = (int)((threads + kBwdBlock - 1) / kBwdBlock);
     const size_t smem = (size_t)(kNumLive + kBwdScratch) * kBwdBlock * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(rollout_bwd_kernel<TERR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    e = upload_model(mc, s);
+    e = upload_model(mc, d_live, s);
     if (e != cudaSuccess) return e;
     rollout_bwd_kernel<TERR><<<grid, kBwdBlock, smem, s>>>(a);
     return cudaGetLastError();

@@ -44,6 +44,9 @@ struct avs_ctx {
     DevBuf ckpt, act, gps, loss, reduced, flags, settle;
     DevBuf in_x0, in_ctrl, in_gt, out_list, out_final, io_a, io_b, io_c;
     long long launches = 0;
+    int plan_N = -1;
+    size_t plan_per_vehicle = 0, plan_chunk = 0;
+    unsigned long long plan_budget = 0;
     std::string err;
 };
 
@@ -80,6 +83,10 @@ static int refresh_params(avs_ctx* ctx) {
     }
     return AVS_OK;
 }
+
+// device copy of the parameter vector is authoritative for the NN weights (kept in sync by avs_set_nn_params and
+// updated in place by the device RMSProp), see upload_model()
+static const double* live(const avs_ctx* c) { return c->tire == AVS_TIRE_NN ? c->d_params : nullptr; }
 
 extern "C" {
 
@@ -251,10 +258,8 @@ int avs_init_state_com(const double* s, double* b) {
 int avs_settle(avs_ctx* ctx, double* state21_out) {
     if (!ctx || !state21_out) return fail(ctx, AVS_E_ARG, "avs_settle: null argument");
     CK(cudaSetDevice(ctx->device));
-    int rc = refresh_params(ctx);
-    if (rc) return rc;
     CK(ctx->settle.reserve(21 * sizeof(double)));
-    CK(launch_settle(ctx->tire, ctx->mc, ctx->settle.as<double>(), ctx->stream));
+    CK(launch_settle(ctx->tire, ctx->mc, live(ctx), ctx->settle.as<double>(), ctx->stream));
     ctx->launches++;
     CK(cudaMemcpyAsync(state21_out, ctx->settle.p, 21 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -264,13 +269,11 @@ int avs_settle(avs_ctx* ctx, double* state21_out) {
 int avs_ode(avs_ctx* ctx, int N, const double* x, const double* u, double* xd) {
     if (!ctx || N <= 0 || !x || !u || !xd) return fail(ctx, AVS_E_ARG, "avs_ode: bad argument");
     CK(cudaSetDevice(ctx->device));
-    int rc = refresh_params(ctx);
-    if (rc) return rc;
     const size_t n = (size_t)N;
     CK(ctx->io_a.reserve(21 * n * 8)); CK(ctx->io_b.reserve(2 * n * 8)); CK(ctx->io_c.reserve(21 * n * 8));
     CK(cudaMemcpyAsync(ctx->io_a.p, x, 21 * n * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->io_b.p, u, 2 * n * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CK(launch_ode(ctx->tire, ctx->mc, N, ctx->io_a.as<double>(), ctx->io_b.as<double>(), ctx->io_c.as<double>(), ctx->stream));
+    CK(launch_ode(ctx->tire, ctx->mc, live(ctx), N, ctx->io_a.as<double>(), ctx->io_b.as<double>(), ctx->io_c.as<double>(), ctx->stream));
     ctx->launches++;
     CK(cudaMemcpyAsync(xd, ctx->io_c.p, 21 * n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -280,13 +283,11 @@ int avs_ode(avs_ctx* ctx, int N, const double* x, const double* u, double* xd) {
 int avs_rollout_dev(avs_ctx* ctx, int N, int T, int substeps, const double* d_x0, const double* d_ctrl, double* d_x_list, double* d_x_final) {
     if (!ctx || N <= 0 || T < 1 || substeps < 1 || !d_x0 || (T > 1 && !d_ctrl)) return fail(ctx, AVS_E_ARG, "avs_rollout: bad argument (N=%d T=%d substeps=%d)", N, T, substeps);
     CK(cudaSetDevice(ctx->device));
-    int rc = refresh_params(ctx);
-    if (rc) return rc;
     RolloutArgs a;
     memset(&a, 0, sizeof(a));
     a.N = N; a.Nc = N; a.T = T; a.substeps = substeps; a.x0 = d_x0; a.ctrl = d_ctrl; a.x_list = d_x_list; a.x_final = d_x_final;
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-    CK(launch_rollout_fwd(ctx->tire, ctx->terr, false, ctx->mc, a, ctx->stream));
+    CK(launch_rollout_fwd(ctx->tire, ctx->terr, false, ctx->mc, live(ctx), a, ctx->stream));
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     ctx->ev_fwd = true; ctx->ev_bwd = false;
     ctx->launches++;
@@ -319,8 +320,6 @@ int avs_rollout_grad_dev(avs_ctx* ctx, int N, int T, int substeps, const double*
         return fail(ctx, AVS_E_ARG, "avs_rollout_grad: bad argument (N=%d T=%d substeps=%d mode=%d)", N, T, substeps, explode_mode);
     if (ctx->tire != AVS_TIRE_NN) return fail(ctx, AVS_E_STATE, "avs_rollout_grad: the adjoint exists for the NN tire model only");
     CK(cudaSetDevice(ctx->device));
-    int rc = refresh_params(ctx);
-    if (rc) return rc;
     const size_t n = (size_t)N;
     if (!d_loss) { CK(ctx->loss.reserve(n * 8)); d_loss = ctx->loss.as<double>(); }
     if (!d_grad_live) { CK(ctx->gps.reserve((size_t)kNumLive * n * 8)); d_grad_live = ctx->gps.as<double>(); }
@@ -328,16 +327,22 @@ int avs_rollout_grad_dev(avs_ctx* ctx, int N, int T, int substeps, const double*
     const size_t per_vehicle_ck = ((size_t)(T - 1) * substeps * 4 + 1) * kCkRows * 8;
     const size_t per_vehicle_act = (size_t)(T - 1) * substeps * 4 * kActLen * 4 * 8;
     const size_t per_vehicle = per_vehicle_ck + per_vehicle_act;
-    size_t budget = ctx->ckpt_budget;
-    if (budget == 0) {
-        size_t free_b = 0, total_b = 0;
-        CK(cudaMemGetInfo(&free_b, &total_b));
-        budget = (size_t)((double)(free_b + ctx->ckpt.cap + ctx->act.cap) * 0.6);
+    size_t chunk;
+    if (ctx->plan_N == N && ctx->plan_per_vehicle == per_vehicle && ctx->plan_budget == ctx->ckpt_budget) {
+        chunk = ctx->plan_chunk;  // same problem shape as the last call: no driver queries on the hot path
+    } else {
+        size_t budget = ctx->ckpt_budget;
+        if (budget == 0) {
+            size_t free_b = 0, total_b = 0;
+            CK(cudaMemGetInfo(&free_b, &total_b));
+            budget = (size_t)((double)(free_b + ctx->ckpt.cap + ctx->act.cap) * 0.6);
+        }
+        chunk = budget / per_vehicle;
+        if (chunk >= n) chunk = n;
+        else chunk = (chunk / 256) * 256;  // whole CTAs
+        ctx->plan_N = N; ctx->plan_per_vehicle = per_vehicle; ctx->plan_budget = ctx->ckpt_budget; ctx->plan_chunk = chunk;
     }
-    size_t chunk = budget / per_vehicle;
-    if (chunk >= n) chunk = n;
-    else chunk = (chunk / 256) * 256;  // whole CTAs
-    if (chunk == 0) return fail(ctx, AVS_E_NOMEM, "avs_rollout_grad: checkpoint budget %zu B < one 256-vehicle chunk (%zu B)", budget, per_vehicle * 256);
+    if (chunk == 0) return fail(ctx, AVS_E_NOMEM, "avs_rollout_grad: the reverse-sweep buffers of one 256-vehicle chunk (%zu B) exceed the memory budget", per_vehicle * 256);
     CK(ctx->ckpt.reserve(chunk * per_vehicle_ck));
     CK(ctx->act.reserve(chunk * per_vehicle_act));
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
@@ -348,9 +353,9 @@ int avs_rollout_grad_dev(avs_ctx* ctx, int N, int T, int substeps, const double*
         a.N = N; a.Nc = (int)cnt; a.T = T; a.substeps = substeps;
         a.x0 = d_x0 + begin; a.ctrl = d_ctrl + begin; a.gt = d_gt + begin; a.ckpt = ctx->ckpt.as<double>(); a.act = ctx->act.as<double>();
         a.loss = d_loss + begin; a.gps = d_grad_live + begin;
-        CK(launch_rollout_fwd(AVS_TIRE_NN, ctx->terr, true, ctx->mc, a, ctx->stream));
+        CK(launch_rollout_fwd(AVS_TIRE_NN, ctx->terr, true, ctx->mc, live(ctx), a, ctx->stream));
         if (begin == 0 && cnt == n) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-        CK(launch_rollout_bwd(ctx->terr, ctx->mc, a, ctx->stream));
+        CK(launch_rollout_bwd(ctx->terr, ctx->mc, live(ctx), a, ctx->stream));
         ctx->launches += 2;
     }
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));

@@ -10,6 +10,7 @@
 // parameter through generic loads; a module-scope __constant__ object keeps every weight a constant-bank
 // operand (c[0x3][imm]) of the DFMA that uses it.
 #pragma once
+#include <cstddef>
 #include "avs_kernels.h"
 
 namespace avs {
@@ -135,9 +136,16 @@ template <int BLOCK> struct CkptStreamAsync {
     }
 };
 
-// upload the model into this TU's __constant__ copy (stream-ordered, before the launch that reads it)
-static inline cudaError_t upload_model(const ModelConst& mc, cudaStream_t s) {
-    return cudaMemcpyToSymbolAsync(c_mc, &mc, sizeof(ModelConst), 0, cudaMemcpyHostToDevice, s);
+// upload the model into this TU's __constant__ copy (stream-ordered, before the launch that reads it).
+// d_live (optional) = device copy of the parameter vector: its first 104 entries (network 0: W0, W2, W4 in the
+// reference pack order) overwrite the head of ModelConst device-to-device, so a device-side RMSProp step needs
+// no host round trip before the next rollout.
+static inline cudaError_t upload_model(const ModelConst& mc, const double* d_live, cudaStream_t s) {
+    static_assert(offsetof(ModelConst, W0) == 0 && offsetof(ModelConst, W2) == 24 * sizeof(double) && offsetof(ModelConst, W4) == 88 * sizeof(double),
+                  "ModelConst must start with W0 | W2 | W4 in the reference pack order");
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_mc, &mc, sizeof(ModelConst), 0, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess || !d_live) return e;
+    return cudaMemcpyToSymbolAsync(c_mc, d_live, kNumLive * sizeof(double), 0, cudaMemcpyDeviceToDevice, s);
 }
 
 }  // namespace avs

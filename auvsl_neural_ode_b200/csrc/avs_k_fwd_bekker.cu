@@ -10,7 +10,7 @@
 namespace avs {
 
 cudaError_t launch_fwd_bekker(const ModelConst& mc, const RolloutArgs& a, cudaStream_t s) {
-    return launch_fwd_t<TIRE_BEKKER, TERR_DYN, false>(mc, a, s);
+    return launch_fwd_t<TIRE_BEKKER, TERR_DYN, false>(mc, nullptr, a, s);
 }
 
 }  // namespace avs

@@ -9,8 +9,8 @@
 
 namespace avs {
 
-cudaError_t launch_fwd_nn_dyn(bool store, const ModelConst& mc, const RolloutArgs& a, cudaStream_t s) {
-    return store ? launch_fwd_t<TIRE_NN, TERR_DYN, true>(mc, a, s) : launch_fwd_t<TIRE_NN, TERR_DYN, false>(mc, a, s);
+cudaError_t launch_fwd_nn_dyn(bool store, const ModelConst& mc, const double* d_live, const RolloutArgs& a, cudaStream_t s) {
+    return store ? launch_fwd_t<TIRE_NN, TERR_DYN, true>(mc, d_live, a, s) : launch_fwd_t<TIRE_NN, TERR_DYN, false>(mc, d_live, a, s);
 }
 
 }  // namespace avs

@@ -65,16 +65,16 @@ __global__ void settle_kernel(double* __restrict__ state21) {
     }
 }
 
-cudaError_t launch_ode(int tire, const ModelConst& mc, int N, const double* x, const double* u, double* xd, cudaStream_t s) {
+cudaError_t launch_ode(int tire, const ModelConst& mc, const double* d_live, int N, const double* x, const double* u, double* xd, cudaStream_t s) {
     const int grid = (int)(((long long)N * 4 + kFwdBlock - 1) / kFwdBlock);
-    cudaError_t e = upload_model(mc, s);
+    cudaError_t e = upload_model(mc, d_live, s);
     if (e != cudaSuccess) return e;
     if (tire == TIRE_NN) ode_kernel<TIRE_NN><<<grid, kFwdBlock, 0, s>>>(N, x, u, xd);
     else ode_kernel<TIRE_BEKKER><<<grid, kFwdBlock, 0, s>>>(N, x, u, xd);
     return cudaGetLastError();
 }
-cudaError_t launch_settle(int tire, const ModelConst& mc, double* st, cudaStream_t s) {
-    cudaError_t e = upload_model(mc, s);
+cudaError_t launch_settle(int tire, const ModelConst& mc, const double* d_live, double* st, cudaStream_t s) {
+    cudaError_t e = upload_model(mc, d_live, s);
     if (e != cudaSuccess) return e;
     const size_t smem = 52 * 32 * sizeof(double);
     if (tire == TIRE_NN) settle_kernel<TIRE_NN><<<1, 32, smem, s>>>(st);

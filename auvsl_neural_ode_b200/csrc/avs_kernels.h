@@ -9,16 +9,16 @@ constexpr int kFwdBlock = 128;  // threads per CTA, forward rollout
 constexpr int kBwdBlock = 32;   // threads per CTA, reverse sweep: (104 gradient + 102 scratch) columns x 32 lanes x 8 B = 52.7 KB, 4 CTAs per SM
 
 // forward rollout: one vehicle per 4-lane group (lane = wheel)
-cudaError_t launch_fwd_nn_flat(bool store, const ModelConst& mc, const RolloutArgs& a, cudaStream_t s);
-cudaError_t launch_fwd_nn_dyn(bool store, const ModelConst& mc, const RolloutArgs& a, cudaStream_t s);
+cudaError_t launch_fwd_nn_flat(bool store, const ModelConst& mc, const double* d_live, const RolloutArgs& a, cudaStream_t s);
+cudaError_t launch_fwd_nn_dyn(bool store, const ModelConst& mc, const double* d_live, const RolloutArgs& a, cudaStream_t s);
 cudaError_t launch_fwd_bekker(const ModelConst& mc, const RolloutArgs& a, cudaStream_t s);
 // reverse sweep (NN tire model only): reads a.ckpt, writes a.loss [Nc] and a.gps [104][stride N]
-cudaError_t launch_bwd_flat(const ModelConst& mc, const RolloutArgs& a, cudaStream_t s);
-cudaError_t launch_bwd_dyn(const ModelConst& mc, const RolloutArgs& a, cudaStream_t s);
+cudaError_t launch_bwd_flat(const ModelConst& mc, const double* d_live, const RolloutArgs& a, cudaStream_t s);
+cudaError_t launch_bwd_dyn(const ModelConst& mc, const double* d_live, const RolloutArgs& a, cudaStream_t s);
 // N independent ODE evaluations: x [21][N], u [2][N] -> xd [21][N]
-cudaError_t launch_ode(int tire, const ModelConst& mc, int N, const double* x, const double* u, double* xd, cudaStream_t s);
+cudaError_t launch_ode(int tire, const ModelConst& mc, const double* d_live, int N, const double* x, const double* u, double* xd, cudaStream_t s);
 // HybridDynamics::settle
-cudaError_t launch_settle(int tire, const ModelConst& mc, double* d_state21, cudaStream_t s);
+cudaError_t launch_settle(int tire, const ModelConst& mc, const double* d_live, double* d_state21, cudaStream_t s);
 // explosion filter + deterministic reduction: gps [104][N], loss [N] -> reduced [418]
 cudaError_t launch_filter_reduce(const double* gps, const double* loss, int N, double thresh, int mode, unsigned char* flags, double* reduced, cudaStream_t s);
 // RMSProp (Trainer::updateParams)
@@ -26,13 +26,13 @@ cudaError_t launch_rmsprop(double* params416, double* sq416, const double* reduc
 // DFMA-chain peak probe
 cudaError_t launch_fp64_peak(int blocks, int threads, int iters, double* sink, cudaStream_t s);
 
-inline cudaError_t launch_rollout_fwd(int tire, int terr, bool store, const ModelConst& mc, const RolloutArgs& a, cudaStream_t s) {
-    if (tire == TIRE_NN) return terr == TERR_FLAT ? launch_fwd_nn_flat(store, mc, a, s) : launch_fwd_nn_dyn(store, mc, a, s);
+inline cudaError_t launch_rollout_fwd(int tire, int terr, bool store, const ModelConst& mc, const double* d_live, const RolloutArgs& a, cudaStream_t s) {
+    if (tire == TIRE_NN) return terr == TERR_FLAT ? launch_fwd_nn_flat(store, mc, d_live, a, s) : launch_fwd_nn_dyn(store, mc, d_live, a, s);
     if (store) return cudaErrorInvalidValue;
     return launch_fwd_bekker(mc, a, s);
 }
-inline cudaError_t launch_rollout_bwd(int terr, const ModelConst& mc, const RolloutArgs& a, cudaStream_t s) {
-    return terr == TERR_FLAT ? launch_bwd_flat(mc, a, s) : launch_bwd_dyn(mc, a, s);
+inline cudaError_t launch_rollout_bwd(int terr, const ModelConst& mc, const double* d_live, const RolloutArgs& a, cudaStream_t s) {
+    return terr == TERR_FLAT ? launch_bwd_flat(mc, d_live, a, s) : launch_bwd_dyn(mc, d_live, a, s);
 }
 
 }  // namespace avs

@@ -54,7 +54,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
             self.t.start()
@@ -252,9 +252,13 @@ def run_b200(args):
         ach_fwd = fwd_flops / (f_ms * 1e-3) / 1e12 if f_ms > 0 else None
         roofline = {
             "bound": "fp64", "kernel": "rollout_bwd_kernel", "achieved": ach_bwd, "peak": fp64_peak, "unit": "TFLOP/s",
-            "frac": (ach_bwd / fp64_peak) if ach_bwd else None, "traffic": None,
+            "frac": (ach_bwd / fp64_peak) if ach_bwd else None,
+            # ncu (profiles/r1_ncu_summary.md): dram read+write of the reverse kernel = 3.02 KB per vehicle-step
+            # (algorithmic: 448 B state records + 2560 B activation records read once)
+            "traffic": 3020.0 * steps_per_call, "traffic_unit": "B per launch", "hbm_frac_of_measured_peak":
+                (3020.0 * steps_per_call / (b_ms * 1e-3) / 1e9 / peaks.get("hbm_gbs", 6543.4)) if b_ms > 0 else None,
             "peak_source": "DFMA-chain microbenchmark run in this process (MEASURED_PEAKS.json has no fp64 entry); "
-                           f"HBM peak of record {peaks.get('hbm_gbs')} GB/s is not the bound: ~0.9 KB of HBM traffic per vehicle-step vs ~77 kflop",
+                           f"HBM peak of record {peaks.get('hbm_gbs')} GB/s is not the bound: ~6 KB of HBM traffic per vehicle-step (fwd writes + bwd reads) vs ~77 kflop-equivalents",
             "kernel_ms": {"rollout_fwd_kernel": f_ms, "rollout_bwd_kernel": b_ms},
             "fwd_kernel": {"achieved": ach_fwd, "frac": (ach_fwd / fp64_peak) if ach_fwd else None},
             "flop_equiv_per_vehicle_step": {"fwd": FLOP_EQ_FWD, "fwd_adjoint": FLOP_EQ_FWD_ADJ},
@@ -278,7 +282,8 @@ def run_b200(args):
             "config": {"workload": f"configs[2] per GPU: {N} rollouts x {T} rows, NN tire model (load_model weights), flat terrain, forward + adjoint "
                                    "w.r.t. tire-NN weights + explosion filter + (all-reduce) + RMSProp",
                        "trajectories_per_gpu": N, "rows": T, "substeps": sub, "vehicle_steps_per_step": world * steps_per_call,
-                       "l2": "no explicit flush: each step streams a 3.6 GB checkpoint buffer (>> 126 MB L2) through HBM",
+                       "l2": "no explicit flush: every step streams 24.5 GB of state + activation records (>> 126 MB L2) out to HBM in the "
+                             "forward sweep and back in the reverse sweep",
                        "parallelism": f"dp{world} (shard by trajectory, one all-reduce of 418 fp64 per step)"},
             "clocks": clocks, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "loss_mean": loss_mean,
