@@ -6,7 +6,7 @@
 namespace avs {
 
 constexpr int kFwdBlock = 128;  // threads per CTA, forward rollout
-constexpr int kBwdBlock = 32;   // threads per CTA, reverse sweep: (104 gradient + 102 scratch) columns x 32 lanes x 8 B = 52.7 KB, 4 CTAs per SM
+constexpr int kBwdBlock = 32;   // (vehicle, wheel) lanes per CTA of the reverse sweep; the CTA has 2 warps (producer + consumer), 44.5 KB smem, 4 CTAs per SM
 
 // forward rollout: one vehicle per 4-lane group (lane = wheel)
 cudaError_t launch_fwd_nn_flat(bool store, const ModelConst& mc, const double* d_live, const RolloutArgs& a, cudaStream_t s);

@@ -432,22 +432,44 @@ AVS_HD void tire_nn_fwd(const ModelConst& mc, double vx, double vy, double w, do
     F[2] = (z4 > 0.0 ? z4 : 0.0) * kOutStd2;  // relu = CondExpGt(x,0,x,0) (TireNetwork.cpp:47-50)
 }
 
-// adjoint: Fbar[3] -> (vx_bar, vy_bar, zr_bar) and dL/dW accumulation through acc.fma(k, a, b): g[k] += a*b
+// The weight gradient of one tire-network evaluation is the sum of three outer products
+//   dW4 += (o0, o1) (x) h2 ,  dW2 += d2 (x) h0 ,  dW0 += d0 (x) (s1, s2, s3)        (pack order of TireNetwork.cpp:130-161)
+// kGradOps = the 37 operands, in this order: o0 o1 | h2[8] | d2[8] | h0[8] | d0[8] | s1 s2 s3.
+constexpr int kGradOps = 37;
+template <class G> AVS_HD void grad_outer(G&& g, const double* op) {
+    const double o0 = op[0], o1 = op[1];
+    const double* h2 = op + 2; const double* d2 = op + 10; const double* h0 = op + 18; const double* d0 = op + 26; const double* sv = op + 34;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { g[kOffW4 + k] = fma(o0, h2[k], g[kOffW4 + k]); g[kOffW4 + 8 + k] = fma(o1, h2[k], g[kOffW4 + 8 + k]); }
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) g[kOffW2 + j * 8 + k] = fma(d2[j], h0[k], g[kOffW2 + j * 8 + k]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) g[kOffW0 + j * 3 + c] = fma(d0[j], sv[c], g[kOffW0 + j * 3 + c]);
+    }
+}
+
+// adjoint: Fbar[3] -> (vx_bar, vy_bar, zr_bar); the operands of the weight-gradient outer products are handed to
+// acc.record(op[37]) — a host accumulator applies grad_outer at once, the device producer warp only stages them for
+// the consumer warp that owns the gradient registers (see avs_bwd_kernel.cuh).
 template <class Acc>
 AVS_HD void tire_nn_bwd(const ModelConst& mc, const NNAct& a, const double Fbar[3], double& vxb, double& vyb, double& zrb, Acc& acc) {
     const double o0 = Fbar[0] * kOutStd0, o1 = Fbar[1] * kOutStd1;
     const double oz = (a.z4 > 0.0) ? Fbar[2] * kOutStd2 : 0.0;  // CondExpGt: derivative 0 at z4 <= 0
-    double d2[8];
+    double op[kGradOps];
+    double* d2 = op + 10; double* d0 = op + 26;
+    op[0] = o0; op[1] = o1;
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        acc.fma(kOffW4 + k, o0, a.h2[k]);
-        acc.fma(kOffW4 + 8 + k, o1, a.h2[k]);
-    }
+    for (int k = 0; k < 8; k++) { op[2 + k] = a.h2[k]; op[18 + k] = a.h0[k]; }
+    op[34] = a.s1; op[35] = a.s2; op[36] = a.s3;
 #pragma unroll
     for (int k = 0; k < 8; k++) d2[k] = fma(mc.W4[1][k], o1, mc.W4[0][k] * o0);
 #pragma unroll
     for (int k = 0; k < 8; k++) d2[k] *= fma(-a.h2[k], a.h2[k], 1.0);
-    double d0[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) d0[k] = mc.W2[0][k] * d2[0];
 #pragma unroll
@@ -457,17 +479,7 @@ AVS_HD void tire_nn_bwd(const ModelConst& mc, const NNAct& a, const double Fbar[
     }
 #pragma unroll
     for (int k = 0; k < 8; k++) d0[k] *= fma(-a.h0[k], a.h0[k], 1.0);
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-#pragma unroll
-        for (int k = 0; k < 8; k++) acc.fma(kOffW2 + j * 8 + k, d2[j], a.h0[k]);
-    }
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-        acc.fma(kOffW0 + j * 3 + 0, d0[j], a.s1);
-        acc.fma(kOffW0 + j * 3 + 1, d0[j], a.s2);
-        acc.fma(kOffW0 + j * 3 + 2, d0[j], a.s3);
-    }
+    acc.record(op);
     double s1a = mc.W0[0][0] * d0[0], s1b = mc.W0[1][0] * d0[1];
     double s3a = mc.W0[0][2] * d0[0], s3b = mc.W0[1][2] * d0[1];
 #pragma unroll
@@ -549,7 +561,7 @@ struct WheelAct {
     double n0, n1, n2;        // I_w * omega_w
 };
 
-struct NullAcc { AVS_HD void fma(int, double, double) {} };
+struct NullAcc { AVS_HD void record(const double*) {} };
 
 // wheel index i: 0 FL(+,+) 1 FR(+,-) 2 RL(-,+) 3 RR(-,-); qd = commanded wheel speed
 template <int TERR>

@@ -19,7 +19,7 @@ struct ArraySink {
 struct HostAcc {
     double g[kNumLive];
     HostAcc() { for (int i = 0; i < kNumLive; i++) g[i] = 0; }
-    void fma(int k, double a, double b) { g[k] += a * b; }
+    void record(const double* op) { grad_outer(g, op); }
 };
 
 static void fill_mc(ModelConst& mc, const double* p416, const double* zw152, const double* bek5, const double* height, const double* soil,
