@@ -33,12 +33,13 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd_kernel(const __grid_c
         // ---------------- producer warp: state adjoint
         double loss;
         int stage_counter = 0;
+        // scratch columns: LAM 0 | YB 13 | KB 26 | record A 39 | record B 53 | activation record 67 ; staging from kBwdSlotG
         auto mk_odeb = [lane0, &stage_counter](double ul, double ur) {
-            return OdeBwdCall<TERR, kBwdBlock>{lane0, 52, 26, 39, kBwdSlotG, ul, ur, 66, 80, &stage_counter};
+            return OdeBwdCall<TERR, kBwdBlock>{lane0, 39, 53, 0, kBwdSlotG, 67, ul, ur, &stage_counter};
         };
         // the stream starts at the final-state record; its (non-existent) activation record is one past the last stage
-        CkptStreamAsync<kBwdBlock> st{a.ckpt + (size_t)nrec * kCkRows * a.Nc + n, (size_t)a.Nc, nrec, 52, 66, 0,
-                                      a.act + ((size_t)nrec * 4 * a.Nc + (size_t)4 * n + lane0) * kActLen, 80};
+        CkptStreamAsync<kBwdBlock> st{a.ckpt + ((size_t)nrec * a.Nc + n) * kCkRows, (size_t)a.Nc * kCkRows, nrec, 39, 53, 0,
+                                      a.act + ((size_t)nrec * 4 * a.Nc + (size_t)4 * n + lane0) * kActLen, (size_t)4 * a.Nc * kActLen, 67};
         st.init();
         rollout_bwd_body(a, n, loss, scratch_col<kBwdBlock>(0), st, mk_odeb);
         if (writer) a.loss[n] = loss;

@@ -67,6 +67,16 @@ template <int BLOCK> struct StagingAcc {
     }
 };
 
+// 14-double record staged in shared memory as seven 16-byte pairs: element c of this lane at
+// base[((c >> 1) * BLOCK) * 2 + (c & 1)]  (base already includes lane * 2)
+template <int BLOCK> struct PairCol {
+    double* base;
+    __device__ __forceinline__ double& operator[](int c) const { return base[(size_t)(c >> 1) * BLOCK * 2 + (c & 1)]; }
+};
+template <int BLOCK> __device__ __forceinline__ PairCol<BLOCK> pair_col(int slot) {
+    return PairCol<BLOCK>{g_smem + (size_t)slot * BLOCK + (size_t)threadIdx.x * 2};
+}
+
 // activation record staged in shared memory as ten 16-byte pairs: pair i of this lane at base[i * BLOCK * 2]
 template <int BLOCK> struct ActInSmem {
     const double* base;
@@ -85,12 +95,14 @@ template <int BLOCK> __device__ __forceinline__ void act_prefetch(int slotACT, c
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-// SB = (df/dX)^T KB at XS, dL/dW += ...
+// adjoint of stage s: LAM += J^T KB through the stage normalisation, KB <- adjoint of the previous stage's k,
+// weight-gradient operands staged for the consumer warp
 template <int TERR, int BLOCK>
-__device__ __noinline__ void ode_bwd_call(int lane0, int slotXS, int slotKB, int slotSB, int slotG, int slotACT, double ul, double ur,
-                                          const double* act_next, int stage_count) {
+__device__ __noinline__ void ode_bwd_call(int lane0, int slotXS, int slotLAM, int slotG, int slotACT, double ul, double ur, const double* act_next,
+                                          int stage_count, int s) {
     // (slotXS is dynamic: the record buffers alternate)
-    const Scratch<BLOCK> XS = scratch_col<BLOCK>(slotXS), KB = scratch_col<BLOCK>(slotKB), SB = scratch_col<BLOCK>(slotSB);
+    const PairCol<BLOCK> XS = pair_col<BLOCK>(slotXS);
+    const Scratch<BLOCK> LAM = scratch_col<BLOCK>(slotLAM), YB = scratch_col<BLOCK>(slotLAM + 13), KB = scratch_col<BLOCK>(slotLAM + 26);
     StagingAcc<BLOCK> acc{g_smem + slotG * BLOCK + threadIdx.x, stage_count};
     double X[13], Xb[13];
 #pragma unroll
@@ -99,18 +111,15 @@ __device__ __noinline__ void ode_bwd_call(int lane0, int slotXS, int slotKB, int
     // record (HBM -> smem, asynchronous; a whole stage of compute later the stream's next advance() waits for it)
     auto refill = [slotACT, act_next]() { if (act_next) act_prefetch<BLOCK>(slotACT, act_next); };
     ode_bwd_nn<1, TERR>(c_mc, lane0, X, ul, ur, KB, Xb, acc, ActInSmem<BLOCK>{g_smem + (size_t)slotACT * BLOCK + (size_t)threadIdx.x * 2}, refill);
-#pragma unroll
-    for (int c = 0; c < 13; c++) SB[c] = Xb[c];
+    rk4_bwd_stage_update(XS, Xb, s, LAM, YB, KB);
 }
 template <int TERR, int BLOCK> struct OdeBwdCall {
-    int lane0, slotXS, slotKB, slotSB, slotG;
+    int lane0, slotXA, slotXB, slotLAM, slotG, slotACT;
     double ul, ur;
-    int slotXB;  // second record buffer
-    int slotACT;
     int* stage_counter;  // stages handed to the consumer warp so far
-    __device__ __forceinline__ void operator()(Scratch<BLOCK> XS, Scratch<BLOCK>, Scratch<BLOCK>, const double* act_next) const {
-        const bool isA = XS.p == scratch_col<BLOCK>(slotXS).p;
-        ode_bwd_call<TERR, BLOCK>(lane0, isA ? slotXS : slotXB, slotKB, slotSB, slotG, slotACT, ul, ur, act_next, (*stage_counter)++);
+    __device__ __forceinline__ void operator()(PairCol<BLOCK> XS, Scratch<BLOCK>, Scratch<BLOCK>, Scratch<BLOCK>, int s, const double* act_next) const {
+        const bool isA = XS.base == pair_col<BLOCK>(slotXA).base;
+        ode_bwd_call<TERR, BLOCK>(lane0, isA ? slotXA : slotXB, slotLAM, slotG, slotACT, ul, ur, act_next, (*stage_counter)++, s);
     }
 };
 
@@ -118,38 +127,39 @@ template <int TERR, int BLOCK> struct OdeBwdCall {
 // record of the stage before it is copied HBM -> this lane's shared-memory column by cp.async (LDGSTS), so the
 // HBM latency of the checkpoint stream is off the critical path of the single resident warp.
 template <int BLOCK> struct CkptStreamAsync {
-    const double* rec;   // current record in HBM
-    size_t stride;
+    const double* rec;   // current record of this vehicle in HBM (14 contiguous doubles)
+    size_t rec_stride;   // doubles between consecutive records = Nc * kCkRows
     long remaining;      // records before the current one
     int slotA, slotB, parity;
     const double* actp;  // this lane's activation record (HBM) of the current stage
+    size_t act_stride;   // doubles between the activation records of consecutive stages = 4 * Nc * kActLen
     int slotACT;
     // token handed to the adjoint call: HBM address of the activation record it should prefetch next
-    __device__ __forceinline__ const double* act() const { return remaining > 0 ? actp - (size_t)kActLen * 4 * stride : nullptr; }
-    __device__ __forceinline__ Scratch<BLOCK> cur() const { return scratch_col<BLOCK>(parity ? slotB : slotA); }
+    __device__ __forceinline__ const double* act() const { return remaining > 0 ? actp - act_stride : nullptr; }
+    __device__ __forceinline__ PairCol<BLOCK> cur() const { return pair_col<BLOCK>(parity ? slotB : slotA); }
     __device__ __forceinline__ void prefetch_prev() {
         if (remaining <= 0) return;
-        const double* src = rec - (size_t)kCkRows * stride;
-        const Scratch<BLOCK> dst = scratch_col<BLOCK>(parity ? slotA : slotB);
+        const double* src = rec - rec_stride;
+        const int slot = parity ? slotA : slotB;
 #pragma unroll
-        for (int c = 0; c < kCkRows; c++) {
-            const unsigned saddr = (unsigned)__cvta_generic_to_shared(&dst[c]);
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(src + (size_t)c * stride) : "memory");
+        for (int i = 0; i < kCkRows / 2; i++) {
+            const unsigned saddr = (unsigned)__cvta_generic_to_shared(g_smem + (size_t)slot * BLOCK + ((size_t)i * BLOCK + threadIdx.x) * 2);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(src + 2 * i) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
     __device__ __forceinline__ void init() {  // synchronous load of the final-state record, then start the pipeline
-        const Scratch<BLOCK> dst = cur();
+        const PairCol<BLOCK> dst = cur();
 #pragma unroll
-        for (int c = 0; c < kCkRows; c++) dst[c] = __ldg(rec + (size_t)c * stride);
+        for (int c = 0; c < kCkRows; c++) dst[c] = __ldg(rec + c);
         prefetch_prev();
-        if (remaining > 0) act_prefetch<BLOCK>(slotACT, actp - (size_t)kActLen * 4 * stride);  // first stage to be reversed
+        if (remaining > 0) act_prefetch<BLOCK>(slotACT, actp - act_stride);  // first stage to be reversed
     }
     __device__ __forceinline__ void advance() {
         asm volatile("cp.async.wait_all;" ::: "memory");
         parity ^= 1;
-        rec -= (size_t)kCkRows * stride;
-        actp -= (size_t)kActLen * 4 * stride;
+        rec -= rec_stride;
+        actp -= act_stride;
         remaining--;
         prefetch_prev();
     }

@@ -56,7 +56,8 @@ __global__ void settle_kernel(double* __restrict__ state21) {
             X[10 + c] = R[c] * lw[0] + R[3 + c] * lw[1] + R[6 + c] * lw[2];
         }
         NullSink sink;
-        rk4_fwd(ode, X, ACC, T, K, sink);
+        double inv_carry = 1.0;
+        rk4_fwd(ode, X, ACC, T, K, sink, inv_carry);
     }
     if (threadIdx.x == 0) {
         for (int c = 0; c < 21; c++) state21[c] = 0.0;

@@ -929,11 +929,10 @@ template <class VX, class VB> AVS_HD void renorm_bwd(const VX& Xn, double inv_no
     Xb[2] = (b2 - x2 * d) * inv_norm; Xb[3] = (b3 - x3 * d) * inv_norm;
 }
 
-// Stage sink: receives every (normalised) stage input and the inverse norm that produced it
-// (stage 0: the inverse norm of the step OUTPUT, delivered by finish()).  NullSink for plain rollouts.
+// Stage sink: receives every (normalised) stage input and the inverse norm that goes into its record (stages 1-3:
+// the norm that produced that stage input; stage 0: the PREVIOUS step's final normalisation).  NullSink for plain rollouts.
 struct NullSink {
     template <class V> AVS_HD void stage(int, const V&, double) {}
-    AVS_HD void finish(double) {}
 };
 
 // One RK4 step.  All loop-carried state lives in per-thread scratch columns (X in/out; ACC, T, K scratch,
@@ -942,8 +941,10 @@ struct NullSink {
 // dependency chains, whereas a stand-alone function body keeps the interleaved (ILP) order it is written in.
 // The four stages run as a rolled loop; the stage weights of HybridDynamics.cpp:470-495 are selected by index.
 template <class Ode, class Sink, class St>
-AVS_HD void rk4_fwd(Ode& ode, St X, St ACC, St T, St K, Sink& sink) {
-    double inv = 1.0;
+AVS_HD void rk4_fwd(Ode& ode, St X, St ACC, St T, St K, Sink& sink, double& inv_carry) {
+    // inv_carry: in = inverse norm of the previous step's final normalisation (rides in this step's stage-0 record),
+    //            out = this step's
+    double inv = inv_carry;
     const double h = kDt;
 #pragma unroll
     for (int c = 0; c < 13; c++) { ACC[c] = 0.0; T[c] = X[c]; }
@@ -962,7 +963,7 @@ AVS_HD void rk4_fwd(Ode& ode, St X, St ACC, St T, St K, Sink& sink) {
     renorm(T, inv);
 #pragma unroll
     for (int c = 0; c < 13; c++) X[c] = T[c];
-    sink.finish(inv);
+    inv_carry = inv;
 }
 
 // Adjoint of one RK4 step over a reverse RECORD STREAM.  The forward sweep stores, per RK4 step, four records
@@ -970,14 +971,14 @@ AVS_HD void rk4_fwd(Ode& ode, St X, St ACC, St T, St K, Sink& sink) {
 // that produced that stage input; slot 13 of a stage-0 record holds the inverse norm of the PREVIOUS step's final
 // normalisation (so that the record that serves as "state after the step" also delivers that step's norm).
 // On entry st.cur() is the record after this step; st.advance() steps to the previous record (and prefetches the
-// one before it).  `odeb(XS, KB, SB, act)`: SB = (df/dX)^T KB at stage input XS (+ weight-gradient accumulation), act = the
-// stage's activation records.
-// LAM (13, in/out) = adjoint of the step output on entry, adjoint of the step input on return.
+// one before it).  `odeb(XS, LAM, YB, KB, s, act)` performs the adjoint of stage s (see rk4_bwd_stage_update; it also
+// accumulates the weight gradient); act = the stage's activation records.
+// LAM (13, in/out) = adjoint of the step output on entry, adjoint of the step input on return; YB, KB scratch.
 template <class OdeB, class Stream, class St>
-AVS_HD void rk4_bwd_nn(OdeB& odeb, Stream& st, St LAM, St YB, St KB, St SB) {
+AVS_HD void rk4_bwd_nn(OdeB& odeb, Stream& st, St LAM, St YB, St KB) {
     const double h = kDt;
     {
-        const St XN = st.cur();
+        const auto XN = st.cur();
         const double inv_n = XN[13];
         renorm_bwd(XN, inv_n, LAM);  // adjoint of Y+ = X + h/6 (k1 + 2k2 + 2k3 + k4) through the final normalisation
     }
@@ -986,19 +987,24 @@ AVS_HD void rk4_bwd_nn(OdeB& odeb, Stream& st, St LAM, St YB, St KB, St SB) {
 #pragma unroll 1
     for (int s = 3; s >= 0; s--) {
         st.advance();
-        const St XS = st.cur();
-        odeb(XS, KB, SB, st.act());
-        if (s > 0) {
-            const double inv_s = XS[13];
-            renorm_bwd(XS, inv_s, SB);  // stage input s = N(X + c_s k_s)
-            const double cs = (s == 3) ? h : .5 * h;
-            const double wk = (s == 1) ? (h / 6.0) : (h / 3.0);  // weight of k_s in the output combination
+        odeb(st.cur(), LAM, YB, KB, s, st.act());  // LAM += J^T KB (through the stage normalisation); KB <- adjoint of k_{s-1}
+    }
+}
+
+// The per-stage update shared by the host functor and the device callee: given sb = (df/dX)^T KB at the stage input
+// XS (record with its inverse norm in slot 13), fold it into the running adjoints.
+template <class XSv, class St>
+AVS_HD void rk4_bwd_stage_update(const XSv& XS, double sb[13], int s, St LAM, St YB, St KB) {
+    const double h = kDt;
+    if (s > 0) {
+        renorm_bwd(XS, XS[13], sb);  // stage input s = N(X + c_s k_s)
+        const double cs = (s == 3) ? h : .5 * h;
+        const double wk = (s == 1) ? (h / 6.0) : (h / 3.0);  // weight of k_s in the output combination
 #pragma unroll
-            for (int c = 0; c < 13; c++) { const double b = SB[c]; LAM[c] += b; KB[c] = fma(cs, b, wk * YB[c]); }
-        } else {
+        for (int c = 0; c < 13; c++) { LAM[c] += sb[c]; KB[c] = fma(cs, sb[c], wk * YB[c]); }
+    } else {
 #pragma unroll
-            for (int c = 0; c < 13; c++) LAM[c] += SB[c];
-        }
+        for (int c = 0; c < 13; c++) LAM[c] += sb[c];
     }
 }
 
@@ -1018,13 +1024,12 @@ template <int WPT, int TIRE, int TERR, bool STORE_ACT> struct OdeFwdInline {
 };
 template <int WPT, int TERR, class Acc> struct OdeBwdInline {
     const ModelConst& mc; int lane0; double ul, ur; Acc& acc;
-    template <class St> AVS_HD void operator()(St XS, St KB, St SB, const double* act) const {
+    template <class XSv, class St> AVS_HD void operator()(const XSv& XS, St LAM, St YB, St KB, int s, const double* act) const {
         double X[13], Xb[13];
 #pragma unroll
         for (int c = 0; c < 13; c++) X[c] = XS[c];
         ode_bwd_nn<WPT, TERR>(mc, lane0, X, ul, ur, KB, Xb, acc, ActInPtr{act});
-#pragma unroll
-        for (int c = 0; c < 13; c++) SB[c] = Xb[c];
+        rk4_bwd_stage_update(XS, Xb, s, LAM, YB, KB);
     }
 };
 

@@ -11,7 +11,7 @@
 //   ctrl    [T-1][2][N]      (vl, vr) applied during macro step i -> i+1 (= traj[i].vl/vr, Trainer.cpp:564-565)
 //   x_list  [T][23][N]       optional: the reference's x_list (row 0 = x0 + controls of row 0)
 //   x_final [21][N]          optional
-//   ckpt    [S*4+1][14][Nc]  one record per RK4 stage (S = (T-1)*substeps steps) + one for the final state:
+//   ckpt    [S*4+1][Nc][14]  one record per RK4 stage (S = (T-1)*substeps steps) + one for the final state:
 //                            13 state entries + the inverse quaternion norm the reverse sweep needs with it.
 //                            This stream replaces the tape (448 B per vehicle-step)
 //   act     [S*4][4*Nc][20]  per-wheel tire-network activation records of every stage (2560 B per vehicle-step):
@@ -48,38 +48,41 @@ AVS_HD double ld(const double* p) {
 
 constexpr int kCkRows = 14;  // 13 live states + 1 inverse norm per stage record
 
-// writes stage records straight to HBM (only the writer lane of a group stores)
+// writes stage records straight to HBM as seven 16-byte pairs (only the writer lane of a group stores)
 struct CkptSink {
-    double* base;  // &ckpt[step*4][0][n]
-    size_t stride; // Nc
+    double* base;  // &ckpt[step*4][n][0]
+    size_t rec_stride;  // doubles between consecutive records = Nc * kCkRows
     bool on;
     template <class V> AVS_HD void stage(int s, const V& T, double inv) {
         if (!on) return;
-        double* p = base + (size_t)s * kCkRows * stride;
-#pragma unroll
-        for (int c = 0; c < 13; c++) p[(size_t)c * stride] = T[c];
-        if (s > 0) p[(size_t)13 * stride] = inv;
+        ckpt_store(base + (size_t)s * rec_stride, T, inv);
     }
-    // the inverse norm of this step's final normalisation rides in slot 13 of the NEXT record (stage 0 of the
-    // next step, or the final-state record)
-    AVS_HD void finish(double inv) {
-        if (on) base[((size_t)4 * kCkRows + 13) * stride] = inv;
+    template <class V> AVS_HD static void ckpt_store(double* p, const V& T, double inv) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+        for (int i = 0; i < 6; i++) reinterpret_cast<double2*>(p)[i] = make_double2(T[2 * i], T[2 * i + 1]);
+        reinterpret_cast<double2*>(p)[6] = make_double2(T[12], inv);
+#else
+        for (int c = 0; c < 13; c++) p[c] = T[c];
+        p[13] = inv;
+#endif
     }
 };
 
 // reverse record stream on the host / generic path: plain loads, no prefetch
 template <class St> struct CkptStreamSimple {
     const double* rec;  // current record in HBM
-    size_t stride;
+    size_t rec_stride;  // doubles between consecutive records
     St buf;             // 14-slot scratch column
     const double* actp; // activation records of the current record's stage (lane-offset applied)
+    size_t act_stride;  // doubles between the activation records of consecutive stages
     AVS_HD const double* act() const { return actp; }
     AVS_HD void load() {
 #pragma unroll
-        for (int c = 0; c < kCkRows; c++) buf[c] = ld(rec + (size_t)c * stride);
+        for (int c = 0; c < kCkRows; c++) buf[c] = ld(rec + c);
     }
     AVS_HD St cur() const { return buf; }
-    AVS_HD void advance() { rec -= (size_t)kCkRows * stride; actp -= (size_t)kActLen * 4 * stride; load(); }
+    AVS_HD void advance() { rec -= rec_stride; actp -= act_stride; load(); }
 };
 
 // live-state index -> reference 21-state index
@@ -103,20 +106,21 @@ AVS_HD void rollout_fwd_body(const RolloutArgs& a, int n, int lane0, bool valid,
         a.x_list[(size_t)21 * N + n] = a.T > 1 ? ld(a.ctrl + n) : 0.0;
         a.x_list[(size_t)22 * N + n] = a.T > 1 ? ld(a.ctrl + N + n) : 0.0;
     }
-    double ul = 0.0, ur = 0.0;
+    double ul = 0.0, ur = 0.0, inv_carry = 1.0;
     for (int i = 1; i < a.T; i++) {
         ul = ld(a.ctrl + ((size_t)(i - 1) * 2 + 0) * N + n);
         ur = ld(a.ctrl + ((size_t)(i - 1) * 2 + 1) * N + n);
         auto ode = mk_ode(ul, ur);
 #pragma unroll 1
         for (int s = 0; s < a.substeps; s++) {
-            if (STORE) ode.act_step = a.act + (((size_t)((size_t)(i - 1) * a.substeps + s) * 4) * (4 * NK) + (size_t)4 * n + lane0) * kActLen;
+            const size_t step = (size_t)(i - 1) * a.substeps + s;
+            if (STORE) ode.act_step = a.act + ((step * 4) * (4 * NK) + (size_t)4 * n + lane0) * kActLen;
             if (STORE) {
-                CkptSink sink{a.ckpt + ((size_t)((size_t)(i - 1) * a.substeps + s) * 4) * kCkRows * NK + n, NK, writer};
-                rk4_fwd(ode, X, ACC, TT, KK, sink);
+                CkptSink sink{a.ckpt + ((step * 4) * NK + n) * kCkRows, NK * kCkRows, writer};
+                rk4_fwd(ode, X, ACC, TT, KK, sink, inv_carry);
             } else {
                 NullSink sink;
-                rk4_fwd(ode, X, ACC, TT, KK, sink);
+                rk4_fwd(ode, X, ACC, TT, KK, sink, inv_carry);
             }
         }
         // joint positions: X[7..10] += (ts/6)(k1 + 2k2 + 2k3 + k4) per RK4 step, k = (vl,vr,vl,vr) (HybridDynamics.cpp:495, 615-618)
@@ -133,11 +137,7 @@ AVS_HD void rollout_fwd_body(const RolloutArgs& a, int n, int lane0, bool valid,
             row[(size_t)21 * N] = 0.0; row[(size_t)22 * N] = 0.0;  // VehicleSystem.cpp:144-147
         }
     }
-    if (STORE && writer) {
-        double* base = a.ckpt + ((size_t)(a.T - 1) * a.substeps * 4) * kCkRows * NK + n;
-#pragma unroll
-        for (int c = 0; c < 13; c++) base[(size_t)c * NK] = X[c];
-    }
+    if (STORE && writer) CkptSink::ckpt_store(a.ckpt + (((size_t)(a.T - 1) * a.substeps * 4) * NK + n) * kCkRows, X, inv_carry);
     if (a.x_final && writer) {
 #pragma unroll
         for (int c = 0; c < 13; c++) a.x_final[(size_t)live_to_ref(c) * N + n] = X[c];
@@ -151,7 +151,7 @@ AVS_HD void rollout_fwd_body(const RolloutArgs& a, int n, int lane0, bool valid,
     }
 }
 
-constexpr int kBwdScratch = 100;  // LAM[13] | YB[13] | KB[13] | SB[13] | record buffer A[14] | record buffer B[14] | activation record[20]
+constexpr int kBwdScratch = 87;  // LAM[13] | YB[13] | KB[13] | record buffer A[14] | record buffer B[14] | activation record[20]
 
 // Reverse sweep over the checkpoints written by rollout_fwd_body<.., STORE=true>.
 //   L = (sum_{i=1}^{T-1} l_i) / T / traj_len   (Trainer.cpp:612-649)
@@ -161,7 +161,7 @@ template <class MkOdeB, class Stream, class St>
 AVS_HD void rollout_bwd_body(const RolloutArgs& a, int n, double& loss_out, St S, Stream& st, MkOdeB mk_odeb) {
     const size_t N = (size_t)a.N;
     const int T = a.T;
-    St LAM = S, YB = S.sub(13), KB = S.sub(26), SB = S.sub(39);
+    St LAM = S, YB = S.sub(13), KB = S.sub(26);
     // traj_len = sum |d(x,y)_gt| ; 0 -> 1   (Trainer.cpp:635-647)
     double traj_len = 0.0;
     {
@@ -181,7 +181,7 @@ AVS_HD void rollout_bwd_body(const RolloutArgs& a, int n, double& loss_out, St S
     for (int i = T - 1; i >= 1; i--) {
         {
             // st.cur() = state of data row i (the state after the step about to be reversed)
-            const St XR = st.cur();
+            const auto XR = st.cur();
             double Xr[13], lam[13];
 #pragma unroll
             for (int c = 0; c < 13; c++) { Xr[c] = XR[c]; lam[c] = 0.0; }
@@ -196,7 +196,7 @@ AVS_HD void rollout_bwd_body(const RolloutArgs& a, int n, double& loss_out, St S
         const double ur = ld(a.ctrl + ((size_t)(i - 1) * 2 + 1) * N + n);
         auto odeb = mk_odeb(ul, ur);
 #pragma unroll 1
-        for (int s = a.substeps - 1; s >= 0; s--) rk4_bwd_nn(odeb, st, LAM, YB, KB, SB);
+        for (int s = a.substeps - 1; s >= 0; s--) rk4_bwd_nn(odeb, st, LAM, YB, KB);
     }
     loss_out = lsum * seed;
 }

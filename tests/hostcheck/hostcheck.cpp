@@ -12,8 +12,7 @@ using namespace avs;
 
 struct ArraySink {
     double St[4][13], inv[4];
-    template <class V> void stage(int s, const V& T, double i) { for (int c = 0; c < 13; c++) St[s][c] = T[c]; if (s > 0) inv[s] = i; }
-    void finish(double i) { inv[0] = i; }
+    template <class V> void stage(int s, const V& T, double i) { for (int c = 0; c < 13; c++) St[s][c] = T[c]; inv[s] = i; }
 };
 
 struct HostAcc {
@@ -53,7 +52,8 @@ template <int TIRE, int TERR> static void rk413(const ModelConst& mc, const doub
     Scratch<1> X{sc}, ACC{sc + 13}, TT{sc + 26}, KK{sc + 39};
     for (int c = 0; c < 13; c++) X[c] = X13[c];
     OdeFwdInline<4, TIRE, TERR, false> ode{mc, 0, u[0], u[1], nullptr, 0};
-    rk4_fwd(ode, X, ACC, TT, KK, sink);
+    double inv_carry = 1.0;
+    rk4_fwd(ode, X, ACC, TT, KK, sink, inv_carry);
     for (int c = 0; c < 13; c++) Xn13[c] = X[c];
     if (stages) memcpy(stages, sink.St, sizeof(sink.St));
 }
@@ -84,7 +84,8 @@ template <int TERR> static void bwd_body(const ModelConst& mc, const RolloutArgs
     double sc[kBwdScratch];
     auto mk = [&mc, &acc](double ul, double ur) { return OdeBwdInline<4, TERR, HostAcc>{mc, 0, ul, ur, acc}; };
     const size_t nrec = (size_t)(a.T - 1) * a.substeps * 4;
-    CkptStreamSimple<Scratch<1>> st{a.ckpt + nrec * kCkRows * a.Nc + n, (size_t)a.Nc, Scratch<1>{sc + 52}, a.act + (nrec * 4 * a.Nc + (size_t)4 * n) * kActLen};
+    CkptStreamSimple<Scratch<1>> st{a.ckpt + (nrec * a.Nc + n) * kCkRows, (size_t)a.Nc * kCkRows, Scratch<1>{sc + 52},
+                                    a.act + (nrec * 4 * a.Nc + (size_t)4 * n) * kActLen, (size_t)4 * a.Nc * kActLen};
     st.load();
     rollout_bwd_body(a, n, loss, Scratch<1>{sc}, st, mk);
 }
