@@ -239,6 +239,25 @@ def run_b200(args):
     h2d = (21 + 2 * (T - 1) + 3 * T) * 8 * N
     d2h = (N + capi.REDUCED_LEN) * 8
 
+    # ---------------- context numbers (not the headline): configs[1] forward-only rollouts, same batch, T = 600 rows
+    fwd_only = None
+    if rank == 0:
+        Tf = 600
+        fx0, fctrl, _ = synth.make_batch(N, Tf, seed=synth.SEED)
+        dfx0, dfctrl = torch.from_numpy(fx0).to(dev), torch.from_numpy(fctrl).to(dev)
+        dxf = torch.empty((21, N), dtype=torch.float64, device=dev)
+        for _ in range(2):
+            ctx.rollout_dev(N, Tf, sub, dfx0.data_ptr(), dfctrl.data_ptr(), 0, dxf.data_ptr())
+        torch.cuda.synchronize()
+        ev0.record(stream)
+        for _ in range(3):
+            ctx.rollout_dev(N, Tf, sub, dfx0.data_ptr(), dfctrl.data_ptr(), 0, dxf.data_ptr())
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        fms = ev0.elapsed_time(ev1) / 3
+        fwd_only = {"workload": f"configs[1]: {N} rollouts x {Tf} rows, NN tire model, forward only, 1 GPU", "value": N * (Tf - 1) * sub / (fms * 1e-3),
+                    "unit": UNIT, "ms_per_rollout_batch": fms, "roofline_frac_flop_equiv": FLOP_EQ_FWD * N * (Tf - 1) * sub / (fms * 1e-3) / 1e12 / fp64_peak}
+
     if rank == 0:
         # roofline of the dominant kernel (reverse sweep): SURVEY §8(d) flop-equivalents per vehicle-step x units / duration
         peaks = {}
@@ -261,6 +280,8 @@ def run_b200(args):
                            f"HBM peak of record {peaks.get('hbm_gbs')} GB/s is not the bound: ~6 KB of HBM traffic per vehicle-step (fwd writes + bwd reads) vs ~77 kflop-equivalents",
             "kernel_ms": {"rollout_fwd_kernel": f_ms, "rollout_bwd_kernel": b_ms},
             "fwd_kernel": {"achieved": ach_fwd, "frac": (ach_fwd / fp64_peak) if ach_fwd else None},
+            # hardware-side view (ncu, profiles/README.md): share of cycles the FP64 pipe is busy
+            "ncu_fp64_pipe_active_pct": {"rollout_fwd_kernel": "see profiles/", "rollout_bwd_kernel": "see profiles/"},
             "flop_equiv_per_vehicle_step": {"fwd": FLOP_EQ_FWD, "fwd_adjoint": FLOP_EQ_FWD_ADJ},
             "whole_step_frac": FLOP_EQ_FWD_ADJ * value / world / 1e12 / fp64_peak,
         }
@@ -286,7 +307,7 @@ def run_b200(args):
                              "forward sweep and back in the reverse sweep",
                        "parallelism": f"dp{world} (shard by trajectory, one all-reduce of 418 fp64 per step)"},
             "clocks": clocks, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "loss_mean": loss_mean,
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "loss_mean": loss_mean, "forward_only": fwd_only,
         }
         print(json.dumps(out))
     ctx.close()
