@@ -86,6 +86,46 @@ def test_rollout_vs_oracle_seeded_ragged_batch(nn):
         assert rel_state_err(xf, xf_o) < STATE_RTOL
 
 
+def test_substeps_and_minimal_windows(nn):
+    """substeps other than the reference's 10 (VehicleSystem.cpp:129), the shortest window (T = 2) and N = 1, forward and adjoint."""
+    nn.set_terrain(capi.FLAT)
+    nn.set_nn_params(P)
+    flat = po.terrain(po.FLAT)
+    for N, T, sub in ((1, 2, 10), (3, 4, 3), (5, 3, 1)):
+        x0, ctrl, gt = synth.make_batch(N, T, seed=200 + N)
+        xl, xf = nn.rollout(x0, ctrl, T, substeps=sub)
+        xl_o, xf_o = po.rollout_batch(po.TIRE_NN, P, flat, x0, ctrl, T, substeps=sub)
+        assert rel_state_err(xl, xl_o) < STATE_RTOL and rel_state_err(xf, xf_o) < STATE_RTOL
+    # the oracle's gradient entry point is fixed at 10 sub-steps, like the reference
+    for N, T in ((1, 2), (1, 7), (2, 3)):
+        x0, ctrl, gt = synth.make_batch(N, T, seed=300 + T)
+        loss, red, gps = nn.rollout_grad(x0, ctrl, gt, T)
+        lo, gs, ls, nk, gps_o = po.rollout_grad_batch(P, flat, x0, ctrl, gt, T)
+        np.testing.assert_allclose(loss, lo, rtol=1e-9)
+        np.testing.assert_allclose(gps, gps_o, rtol=GRAD_RTOL, atol=1e-11 * np.abs(gps_o).max())
+        assert red[417] == N
+
+
+def test_zero_trajectory_length_and_zero_params(nn):
+    """traj_len == 0 -> divisor 1 (Trainer.cpp:643-647); all-zero network (the reference's test_wz setup) gives a zero-force vehicle."""
+    flat = po.terrain(po.FLAT)
+    N, T = 2, 4
+    x0, ctrl, gt = synth.make_batch(N, T, seed=5)
+    gt[:, 1:, :] = 0.25  # constant ground-truth position -> traj_len = 0
+    nn.set_nn_params(P)
+    loss, red, gps = nn.rollout_grad(x0, ctrl, gt, T)
+    lo, gs, ls, nk, gps_o = po.rollout_grad_batch(P, flat, x0, ctrl, gt, T)
+    np.testing.assert_allclose(loss, lo, rtol=1e-9)
+    np.testing.assert_allclose(gps, gps_o, rtol=GRAD_RTOL, atol=1e-11 * np.abs(gps_o).max())
+    pz = np.zeros(416)
+    nn.set_nn_params(pz)
+    x = np.zeros((21, 1)); x[3] = 1; x[6] = 100; x[13] = 10
+    xl, xf = nn.rollout(x, np.zeros((9, 2, 1)), 10)
+    xl_o, xf_o = po.rollout_batch(po.TIRE_NN, pz, flat, x, np.zeros((9, 2, 1)), 10)
+    assert rel_state_err(xf, xf_o) < STATE_RTOL
+    nn.set_nn_params(P)
+
+
 def test_rollout_T1_returns_initial_state(nn):
     x0, ctrl, _ = synth.make_batch(4, 2, seed=1)
     xl, xf = nn.rollout(x0, np.zeros((0, 2, 4)), 1)
