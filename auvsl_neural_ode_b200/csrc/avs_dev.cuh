@@ -43,6 +43,56 @@ template <int TIRE, int TERR, int BLOCK, bool STORE_ACT> struct OdeFwdCall {
     }
 };
 
+// ---- fused forward stage (NN kernels): one non-inlined call = store the stage record, evaluate K = f(T), and apply the
+// RK4 stage update of HybridDynamics.cpp:470-500 (same arithmetic and order as rk4_fwd in avs_model.cuh), so that the
+// rolled loop in the kernel contains nothing but four calls.  Scratch slots: X 0 | ACC 13 | T 26 | INV 56.
+template <int TERR, int BLOCK, bool STORE>
+__device__ __noinline__ void ode_fwd_stage_call(int lane0, double ul, double ur, int s, double* rec, double* act) {
+    const Scratch<BLOCK> X = scratch_col<BLOCK>(0), ACC = scratch_col<BLOCK>(13), T = scratch_col<BLOCK>(26), INV = scratch_col<BLOCK>(56);
+    double x[13], k[13];
+#pragma unroll
+    for (int c = 0; c < 13; c++) x[c] = T[c];
+    if (STORE && rec) CkptSink::ckpt_store(rec, x, INV[0]);
+    ode_fwd<1, TIRE_NN, TERR, STORE>(c_mc, lane0, x, ul, ur, k, nullptr, ActOutPtr{act});
+    const double h = kDt;
+    double inv;
+    if (s < 3) {
+        const double wgt = (s == 0) ? 1.0 : 2.0;   // k1 + 2 k2 + 2 k3 + k4
+        const double cs = (s == 2) ? h : .5 * h;   // X + .5h k1, X + .5h k2, X + h k3
+#pragma unroll
+        for (int c = 0; c < 13; c++) {
+            ACC[c] = (s == 0) ? fma(wgt, k[c], 0.0) : fma(wgt, k[c], ACC[c]);
+            x[c] = fma(cs, k[c], X[c]);
+        }
+        renorm(x, inv);
+#pragma unroll
+        for (int c = 0; c < 13; c++) T[c] = x[c];
+    } else {
+#pragma unroll
+        for (int c = 0; c < 13; c++) x[c] = fma(h / 6.0, fma(1.0, k[c], ACC[c]), X[c]);
+        renorm(x, inv);
+#pragma unroll
+        for (int c = 0; c < 13; c++) { X[c] = x[c]; T[c] = x[c]; }
+    }
+    INV[0] = inv;
+}
+template <int TERR, int BLOCK, bool STORE> struct FusedStep {
+    const RolloutArgs& a;
+    int n, lane0;
+    bool writer;
+    double ul, ur;
+    __device__ __forceinline__ void operator()(size_t step, double& inv_carry) const {
+        const size_t NK = (size_t)a.Nc;
+        double* rec = (STORE && writer) ? a.ckpt + ((step * 4) * NK + n) * kCkRows : nullptr;
+        double* act = STORE ? a.act + ((step * 4) * (4 * NK) + (size_t)4 * n + lane0) * kActLen : nullptr;
+        const size_t rec_stride = NK * kCkRows, act_stride = (size_t)4 * NK * kActLen;
+#pragma unroll 1
+        for (int s = 0; s < 4; s++)
+            ode_fwd_stage_call<TERR, BLOCK, STORE>(lane0, ul, ur, s, rec ? rec + (size_t)s * rec_stride : nullptr, STORE ? act + (size_t)s * act_stride : nullptr);
+        inv_carry = scratch_col<BLOCK>(56)[0];
+    }
+};
+
 // ---- producer / consumer hand-off of the weight-gradient operands ---------------------------------------
 // The reverse kernel is warp-specialised: warp 0 of a CTA (producer) runs the state adjoint, warp 1 (consumer)
 // owns the 104 gradient accumulators IN REGISTERS and does nothing but  g += outer products.  Per RK4 stage the

@@ -11,9 +11,26 @@ __global__ void __launch_bounds__(kFwdBlock) rollout_fwd_kernel(const __grid_con
     const int lane0 = gid & 3;
     const bool valid = n < a.Nc;
     if (!valid) n = a.Nc - 1;  // tail lanes mirror the last vehicle so that group shuffles stay converged
-    const size_t stage_stride = (size_t)4 * a.Nc * kActLen;
-    auto mk_ode = [lane0, stage_stride](double ul, double ur) { return OdeFwdCall<TIRE, TERR, kFwdBlock, STORE && TIRE == TIRE_NN>{lane0, 26, 39, ul, ur, nullptr, stage_stride}; };
-    rollout_fwd_body<STORE>(a, n, lane0, valid, scratch_col<kFwdBlock>(0), mk_ode);
+    const Scratch<kFwdBlock> S = scratch_col<kFwdBlock>(0);
+    const bool writer = (lane0 == 0) && valid;
+    if (TIRE == TIRE_NN) {
+        // fused stages: T starts as a copy of X, the carried inverse norm as 1
+        {
+            const size_t N = (size_t)a.N;
+#pragma unroll
+            for (int c = 0; c < 13; c++) S[26 + c] = __ldg(a.x0 + (size_t)live_to_ref(c) * N + n);
+            S[56] = 1.0;
+        }
+        auto mk_step = [&a, n, lane0, writer](double ul, double ur) { return FusedStep<TERR, kFwdBlock, STORE>{a, n, lane0, writer, ul, ur}; };
+        rollout_fwd_body<STORE>(a, n, lane0, valid, S, mk_step);
+    } else {
+        const size_t stage_stride = (size_t)4 * a.Nc * kActLen;
+        auto mk_step = [&a, n, lane0, writer, S, stage_stride](double ul, double ur) {
+            typedef OdeFwdCall<TIRE, TERR, kFwdBlock, false> Ode;
+            return GenericStep<false, Ode, Scratch<kFwdBlock>>{Ode{lane0, 26, 39, ul, ur, nullptr, stage_stride}, a, n, lane0, writer, S};
+        };
+        rollout_fwd_body<false>(a, n, lane0, valid, S, mk_step);
+    }
 }
 
 template <int TIRE, int TERR, bool STORE>

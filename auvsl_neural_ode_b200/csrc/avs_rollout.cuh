@@ -88,14 +88,37 @@ template <class St> struct CkptStreamSimple {
 // live-state index -> reference 21-state index
 AVS_HD constexpr int live_to_ref(int c) { return c < 7 ? c : c + 4; }
 
-constexpr int kFwdScratch = 56;  // X[13] | ACC[13] | T[13] | K[13] | joint positions[4]
+constexpr int kFwdScratch = 57;  // X[13] | ACC[13] | T[13] | K[13] | joint positions[4] | inverse norm carried between stages[1]
 
-// S = per-thread scratch column with kFwdScratch slots; mk_ode(ul, ur) returns the functor K = f(T)
-template <bool STORE, class MkOde, class St>
-AVS_HD void rollout_fwd_body(const RolloutArgs& a, int n, int lane0, bool valid, St S, MkOde mk_ode) {
+// One RK4 step of one vehicle on its scratch columns, generic version: rk4_fwd around an ODE functor (host harness:
+// inline ODE; device Bekker / settle: non-inlined ODE call).  The fused device step of the NN kernels lives in
+// avs_dev.cuh (FusedStep) and does the same arithmetic with the stage update inside the non-inlined callee.
+template <bool STORE, class Ode, class St> struct GenericStep {
+    Ode ode;
+    const RolloutArgs& a;
+    int n, lane0;
+    bool writer;
+    St S;
+    AVS_HD void operator()(size_t step, double& inv_carry) {
+        const size_t NK = (size_t)a.Nc;
+        St X = S, ACC = S.sub(13), TT = S.sub(26), KK = S.sub(39);
+        if (STORE) {
+            ode.act_step = a.act + ((step * 4) * (4 * NK) + (size_t)4 * n + lane0) * kActLen;
+            CkptSink sink{a.ckpt + ((step * 4) * NK + n) * kCkRows, NK * kCkRows, writer};
+            rk4_fwd(ode, X, ACC, TT, KK, sink, inv_carry);
+        } else {
+            NullSink sink;
+            rk4_fwd(ode, X, ACC, TT, KK, sink, inv_carry);
+        }
+    }
+};
+
+// S = per-thread scratch column with kFwdScratch slots; mk_step(ul, ur) returns the RK4-step functor for a macro step
+template <bool STORE, class MkStep, class St>
+AVS_HD void rollout_fwd_body(const RolloutArgs& a, int n, int lane0, bool valid, St S, MkStep mk_step) {
     const size_t N = (size_t)a.N, NK = (size_t)a.Nc;
     const bool writer = (lane0 == 0) && valid;
-    St X = S, ACC = S.sub(13), TT = S.sub(26), KK = S.sub(39), JP = S.sub(52);
+    St X = S, JP = S.sub(52);
 #pragma unroll
     for (int c = 0; c < 13; c++) X[c] = ld(a.x0 + (size_t)live_to_ref(c) * N + n);
 #pragma unroll
@@ -110,19 +133,9 @@ AVS_HD void rollout_fwd_body(const RolloutArgs& a, int n, int lane0, bool valid,
     for (int i = 1; i < a.T; i++) {
         ul = ld(a.ctrl + ((size_t)(i - 1) * 2 + 0) * N + n);
         ur = ld(a.ctrl + ((size_t)(i - 1) * 2 + 1) * N + n);
-        auto ode = mk_ode(ul, ur);
+        auto step = mk_step(ul, ur);
 #pragma unroll 1
-        for (int s = 0; s < a.substeps; s++) {
-            const size_t step = (size_t)(i - 1) * a.substeps + s;
-            if (STORE) ode.act_step = a.act + ((step * 4) * (4 * NK) + (size_t)4 * n + lane0) * kActLen;
-            if (STORE) {
-                CkptSink sink{a.ckpt + ((step * 4) * NK + n) * kCkRows, NK * kCkRows, writer};
-                rk4_fwd(ode, X, ACC, TT, KK, sink, inv_carry);
-            } else {
-                NullSink sink;
-                rk4_fwd(ode, X, ACC, TT, KK, sink, inv_carry);
-            }
-        }
+        for (int s = 0; s < a.substeps; s++) step((size_t)(i - 1) * a.substeps + s, inv_carry);
         // joint positions: X[7..10] += (ts/6)(k1 + 2k2 + 2k3 + k4) per RK4 step, k = (vl,vr,vl,vr) (HybridDynamics.cpp:495, 615-618)
         const double il = (kDt / 6.0) * (((ul + 2 * ul) + 2 * ul) + ul);
         const double ir = (kDt / 6.0) * (((ur + 2 * ur) + 2 * ur) + ur);

@@ -73,10 +73,12 @@ template <int TIRE, int TERR> static void fwd_body(const ModelConst& mc, const R
     double sc[kFwdScratch];
     const size_t stage_stride = (size_t)4 * a.Nc * kActLen;
     if (store) {
-        auto mk = [&mc, stage_stride](double ul, double ur) { return OdeFwdInline<4, TIRE, TERR, TIRE == 0>{mc, 0, ul, ur, nullptr, stage_stride}; };
+        typedef OdeFwdInline<4, TIRE, TERR, TIRE == 0> Ode;
+        auto mk = [&](double ul, double ur) { return GenericStep<true, Ode, Scratch<1>>{Ode{mc, 0, ul, ur, nullptr, stage_stride}, a, n, 0, true, Scratch<1>{sc}}; };
         rollout_fwd_body<true>(a, n, 0, true, Scratch<1>{sc}, mk);
     } else {
-        auto mk = [&mc](double ul, double ur) { return OdeFwdInline<4, TIRE, TERR, false>{mc, 0, ul, ur, nullptr, 0}; };
+        typedef OdeFwdInline<4, TIRE, TERR, false> Ode;
+        auto mk = [&](double ul, double ur) { return GenericStep<false, Ode, Scratch<1>>{Ode{mc, 0, ul, ur, nullptr, 0}, a, n, 0, true, Scratch<1>{sc}}; };
         rollout_fwd_body<false>(a, n, 0, true, Scratch<1>{sc}, mk);
     }
 }
