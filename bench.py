@@ -113,7 +113,7 @@ def run_reference(args):
     from oracle import pyoracle as po
     cores = po.hardware_threads() or os.cpu_count() or 1
     T = args.rows
-    n_traj = 2 * cores
+    n_traj = 8 * cores  # a bounded sample per step (a few seconds), so the whole run ends within minutes
     for _ in range(max(args.warmup, 0) and 1):  # one short warm-up pass is enough for a CPU code path
         cpu_baseline_fwd_adj(min(T, 20), cores, cores)
     t0 = time.perf_counter()
@@ -289,7 +289,7 @@ def run_b200(args):
         if not args.no_cpu_baseline:
             from oracle import pyoracle as po
             cores = po.hardware_threads() or os.cpu_count() or 1
-            n_traj = 4 * cores
+            n_traj = 32 * cores  # ~10 s of CPU work on all host threads
             v_all, dt_all = cpu_baseline_fwd_adj(T, cores, n_traj)
             v_one, dt_one = cpu_baseline_fwd_adj(T, 1, 2)
             cpu = {"value": v_all, "unit": UNIT, "cores": cores, "kind": "port",

@@ -125,6 +125,32 @@ double orc_train_trajectory_monolithic(const double* p416, const orc_terrain* t,
     toRows(rows, T, traj);
     return trainTrajectoryMonolithic(mkTerrain(t), p416, traj.data(), T, grad416);
 }
+// Reverse sweep through ONE BekkerSystem::integrate (BekkerSystem.cpp:145-178) on the tape scalar, as
+// train_bekker.cpp would run it inside Trainer::trainTrajectory:  grad5 = (dx1/dp)^T lambda, xbar = (dx1/dx0)^T lambda.
+// Returns the number of non-finite entries among grad5 and xbar (see tests/test_oracle.py: the reference's
+// Bekker gradient is not finite whenever ze == zr, because theta_c = acos(1) is differentiated at 1).
+int orc_bekker_integrate_vjp(const double* p5, const orc_terrain* t, const double* X23, const double* lambda21, double* x1_23, double* grad5,
+                             double* xbar21) {
+    Tape tape;
+    Tape* prev = active_tape();
+    active_tape() = &tape;
+    Rev P[5], xin[23], xout[23];
+    for (int k = 0; k < 5; k++) P[k] = Rev::independent(p5[k]);
+    for (int k = 0; k < 21; k++) xin[k] = Rev::independent(X23[k]);
+    xin[21] = Rev(X23[21]); xin[22] = Rev(X23[22]);
+    VehicleSystem<Rev> sys(TIRE_BEKKER, mkTerrain(t));
+    sys.setParams(P);
+    sys.integrate(xin, xout);
+    std::vector<double> adj(tape.nodes.size(), 0.0);
+    for (int k = 0; k < 21; k++) if (xout[k].id >= 0) adj[xout[k].id] += lambda21[k];
+    tape.reverse(adj);
+    int bad = 0;
+    for (int k = 0; k < 5; k++) { grad5[k] = adj[P[k].id]; bad += !std::isfinite(grad5[k]); }
+    for (int k = 0; k < 21; k++) { xbar21[k] = adj[xin[k].id]; bad += !std::isfinite(xbar21[k]); }
+    for (int k = 0; k < 23; k++) x1_23[k] = xout[k].v;
+    active_tape() = prev;
+    return bad;
+}
 // forward-mode directional check: d loss / d p[idx[k]] for k < 8, via Dual<8>
 double orc_train_trajectory_dual8(const double* p416, const orc_terrain* t, const double* rows, int T, const int* idx8, double* dloss8) {
     typedef Dual<8> D;

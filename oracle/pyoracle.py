@@ -197,6 +197,15 @@ def train_trajectory_monolithic(p416, t, rows):
     return L, g
 
 
+def bekker_integrate_vjp(p5, t, x23, lam21):
+    """Reverse sweep through one Bekker integrate(): (x1[23], grad5, xbar21, number of non-finite entries)."""
+    p5, x23, lam21 = _f64(p5), _f64(x23), _f64(lam21)
+    x1, g, xb = np.zeros(23), np.zeros(5), np.zeros(21)
+    lib().orc_bekker_integrate_vjp.restype = C.c_int
+    bad = lib().orc_bekker_integrate_vjp(_p(p5), C.byref(t), _p(x23), _p(lam21), _p(x1), _p(g), _p(xb))
+    return x1, g, xb, bad
+
+
 def train_trajectory_dual8(p416, t, rows, idx8):
     p416, rows = _f64(p416), _f64(rows)
     idx = np.ascontiguousarray(idx8, dtype=np.int32)

@@ -315,3 +315,33 @@ def test_argument_errors(nn):
     with pytest.raises(capi.AvsError):
         b.rollout_grad(x0, ctrl, gt, 5)  # adjoint exists for the NN model only
     b.close()
+
+
+def test_safety_sweep_matches_oracle(nn):
+    """the reference's 10 x 10 (vl, vr) safety sweep over BumpyTerrainMap (test/test_Terrain.cpp:71-122,
+    213-346) as one batched rollout; tilt angles and failure rows against the oracle (600 rows instead of 1000: the
+    fastest rollouts are on the bump by then)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("safety_sweep", os.path.join(os.path.dirname(__file__), "..", "scripts", "safety_sweep.py"))
+    ss = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ss)
+    rows = 600
+    nn.set_nn_params(P)
+    nn.set_terrain(capi.BUMPY)
+    x = nn.settle()
+    x_o = po.settle(po.TIRE_NN, P, po.terrain(po.BUMPY))
+    assert rel_state_err(x, x_o) < STATE_RTOL
+    x[4] = x[5] = 0.0
+    x[7:] = 0.0
+    x0, ctrl = ss.sweep_inputs(x, rows)
+    xl, _ = nn.rollout(x0, ctrl, rows + 1, want_final=False)
+    xl_o, _ = po.rollout_batch(po.TIRE_NN, P, po.terrain(po.BUMPY), x0, ctrl, rows + 1, nthreads=16)
+    nn.set_terrain(capi.FLAT)
+    ang, length = ss.safety(xl)
+    ang_o, length_o = ss.safety(xl_o)
+    np.testing.assert_array_equal(length, length_o)
+    np.testing.assert_allclose(ang, ang_o, rtol=0, atol=1e-9)
+    ok = length == rows  # compare states only while the rollout counts (a tipped-over vehicle is chaotic afterwards)
+    assert ok.sum() > 50
+    assert rel_state_err(xl[:, :, ok], xl_o[:, :, ok]) < STATE_RTOL
+    assert ang.max() > 0.1  # some rollouts climbed the bump

@@ -193,3 +193,23 @@ def test_explosion_filter_modes():
     np.testing.assert_allclose(gs0, ref0, rtol=1e-13, atol=1e-18)
     keep = np.abs(gps).max(axis=0) <= thresh * 0.999
     np.testing.assert_allclose(gs1, gps[:, keep].sum(axis=1), rtol=1e-13, atol=1e-18)
+
+
+def test_bekker_reverse_sweep_is_not_finite():
+    """SURVEY.md §8 row (f3), Bekker adjoint: with CppAD's conventions the reverse sweep through one
+    BekkerSystem::integrate is NOT finite in the ordinary ze == zr regime — theta_c = acos(1 - (zr - ze)/R)
+    (BekkerTireModel.cpp:232-238) is differentiated at acos(1).  This is what the reference's notes report
+    ("You can't train the bekker model", todo.org:60; "the param -> nan", todo.org:1088) and why the
+    CUDA path declines rollout_grad for the Bekker tire model instead of inventing a gradient."""
+    p = po.bekker_default_params()
+    st = po.settle(po.TIRE_BEKKER, p, FLAT)
+    x = np.zeros(23)
+    x[:21] = st
+    x[17:21] = 0.0
+    x[21], x[22] = 2.0, 3.0
+    lam = np.zeros(21)
+    lam[4], lam[5] = 1.0, 0.5
+    x1, g, xb, bad = po.bekker_integrate_vjp(p, FLAT, x, lam)
+    assert np.all(np.isfinite(x1))        # the forward values are fine
+    assert bad > 0 and not np.all(np.isfinite(g))
+    assert g[3] == 0.0                    # CondExpGt(p3, 0, p3, 0) at the default p3 = 0 selects the constant branch
