@@ -54,3 +54,64 @@ def test_synth_demo_runs_and_matches_python_path(tmp_path):
     loss, red, _ = ctx.rollout_grad(x0, ctrl, gt, T, explode_mode=1, per_sample=False)
     assert red[416] / red[417] == pytest.approx(avg[0], rel=1e-5)  # the demo prints 6 significant digits
     ctx.close()
+
+
+def _write_log(fn, rows, seed):
+    """Synthetic Jackal log in the reference's CSV schema (Trainer.cpp:102-143), linear kinematic model of the
+    reference's scripts/gen_fake_data.py."""
+    rng = np.random.default_rng(seed)
+    B = np.array([[0.0472, 0.0438], [0.0036, -0.0035], [-0.1744, 0.1748]])
+    vbar, dl, f, ph = 2 + 4 * rng.random(), 2 * rng.random() - 1, 0.05 + 0.4 * rng.random(), 6.28 * rng.random()
+    x = y = yaw = 0.0
+    out = np.zeros((rows, 12))
+    for i in range(rows):
+        t = 0.01 * i
+        vl, vr = vbar + dl + np.sin(6.28 * f * t + ph), vbar - dl + np.sin(6.28 * f * t)
+        vx, vy, wz = B @ np.array([vl, vr])
+        out[i] = (i, t, vl, vr, x, y, yaw, 0, 0, wz, vx, vy)
+        for _ in range(10):
+            x += 1e-3 * (np.cos(yaw) * vx - np.sin(yaw) * vy)
+            y += 1e-3 * (np.sin(yaw) * vx + np.cos(yaw) * vy)
+            yaw += 1e-3 * wz
+    np.savetxt(fn, out, delimiter=",", header=",time,vel_left,vel_right,x,y,yaw,wx,wy,wz,vx,vy", comments="", fmt="%.17g")
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("main,model", [("evaluate", 0), ("evaluate_bekker", 1)])
+def test_reference_evaluate_mains_run_unchanged_and_match_oracle(tmp_path, main, model):
+    """The reference's own evaluate.cpp / evaluate_bekker.cpp — compiled UNCHANGED against the drop-in headers
+    (`make refcheck`, binaries built where /root/reference exists) — run on the GPU against synthetic logs; the
+    losses they print must equal the oracle's Trainer::evaluateTrajectory on the same 600-row windows."""
+    from oracle import pyoracle as po
+    exe = os.path.join(HOST, "_refcheck", main)
+    if not os.path.exists(exe):
+        pytest.skip("prebuilt _refcheck binaries absent (they need the reference sources at build time)")
+    d = str(tmp_path) + "/"
+    logs = {"LD3_data01.csv": _write_log(d + "LD3_data01.csv", 1900, 5)}
+    for i in (1, 2, 17):
+        logs[f"Train3_data{i:02d}.csv"] = _write_log(d + f"Train3_data{i:02d}.csv", 1300, 40 + i)
+    logs["CV3_data01.csv"] = _write_log(d + "CV3_data01.csv", 1250, 90)
+    env = dict(os.environ, AVSL_DATA_DIR=d, AVSL_PARAM_FILE=d + "none.net")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=900, env=env)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    params = po.nn_default_params() if model == 0 else po.bekker_default_params()
+    flat = po.terrain(po.FLAT)
+    z = po.settle(model, params, flat)[6]
+
+    def oracle_losses(a):
+        res = []
+        for j in range(0, a.shape[0] - 600, 600):
+            w = a[j:j + 600]
+            rows = np.stack([w[:, 1], w[:, 2], w[:, 3], w[:, 4], w[:, 5], np.full(600, z), w[:, 6], w[:, 9], w[:, 10], w[:, 11]], axis=1)
+            res.append(po.evaluate_trajectory(model, params, flat, rows)[0])
+        return res
+
+    tol = 2e-5  # the mains print 6 significant digits
+    ld3 = float(re.search(r"LD3 avg loss: ([-+0-9.eE]+)", out.stdout).group(1))
+    assert ld3 == pytest.approx(np.mean(oracle_losses(logs["LD3_data01.csv"])), rel=tol)
+    cv3 = [float(x) for x in re.findall(r"CV3 \d+ loss: ([-+0-9.eE]+)", out.stdout)]
+    assert cv3 == pytest.approx(oracle_losses(logs["CV3_data01.csv"]), rel=tol)
+    tr3 = float(re.search(r"Train3 avg loss: ([-+0-9.eE]+)", out.stdout).group(1))
+    want = [l for i in (1, 2, 17) for l in oracle_losses(logs[f"Train3_data{i:02d}.csv"])]
+    assert tr3 == pytest.approx(np.mean(want), rel=tol)
