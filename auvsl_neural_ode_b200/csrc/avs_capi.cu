@@ -33,6 +33,8 @@ struct avs_ctx {
     unsigned long long ckpt_budget = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // host-buffer entry points: H2D of the ground truth overlaps the forward sweep
+    cudaEvent_t ev_copy = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool ev_fwd = false, ev_bwd = false;
     ModelConst mc;
@@ -139,6 +141,8 @@ int avs_create(avs_ctx** out, int device, int tire_model) {
     ctx->mc.grid.inv_dx = ctx->mc.grid.inv_dy = 1.0;
     bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
     ctx->stream = ctx->own_stream;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < 4 && ok; i++) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_params, sizeof(double) * AVS_NUM_NN_PARAMS) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_sq, sizeof(double) * AVS_NUM_NN_PARAMS) == cudaSuccess;
@@ -164,6 +168,8 @@ void avs_destroy(avs_ctx* ctx) {
     if (ctx->d_params) cudaFree(ctx->d_params);
     if (ctx->d_sq) cudaFree(ctx->d_sq);
     for (int i = 0; i < 4; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -314,8 +320,10 @@ int avs_rollout(avs_ctx* ctx, int N, int T, int substeps, const double* x0, cons
     return AVS_OK;
 }
 
-int avs_rollout_grad_dev(avs_ctx* ctx, int N, int T, int substeps, const double* d_x0, const double* d_ctrl, const double* d_gt, double explode_thresh,
-                         int explode_mode, double* d_loss, double* d_reduced, double* d_grad_live) {
+// host_gt (optional): ground truth still in host memory; it is copied into d_gt on the copy stream AFTER the first
+// forward sweep has been enqueued (only the reverse sweep reads it), so the copy runs under the forward kernel.
+static int rollout_grad_impl(avs_ctx* ctx, int N, int T, int substeps, const double* d_x0, const double* d_ctrl, const double* d_gt, double explode_thresh,
+                             int explode_mode, double* d_loss, double* d_reduced, double* d_grad_live, const double* host_gt) {
     if (!ctx || N <= 0 || T < 2 || substeps < 1 || !d_x0 || !d_ctrl || !d_gt || (explode_mode != 0 && explode_mode != 1))
         return fail(ctx, AVS_E_ARG, "avs_rollout_grad: bad argument (N=%d T=%d substeps=%d mode=%d)", N, T, substeps, explode_mode);
     if (ctx->tire != AVS_TIRE_NN) return fail(ctx, AVS_E_STATE, "avs_rollout_grad: the adjoint exists for the NN tire model only");
@@ -355,6 +363,11 @@ int avs_rollout_grad_dev(avs_ctx* ctx, int N, int T, int substeps, const double*
         a.loss = d_loss + begin; a.gps = d_grad_live + begin;
         CK(launch_rollout_fwd(AVS_TIRE_NN, ctx->terr, true, ctx->mc, live(ctx), a, ctx->stream));
         if (begin == 0 && cnt == n) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+        if (begin == 0 && host_gt) {
+            CK(cudaMemcpyAsync(const_cast<double*>(d_gt), host_gt, (size_t)T * 3 * n * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+            CK(cudaEventRecord(ctx->ev_copy, ctx->copy_stream));
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy, 0));
+        }
         CK(launch_rollout_bwd(ctx->terr, ctx->mc, live(ctx), a, ctx->stream));
         ctx->launches += 2;
     }
@@ -368,6 +381,11 @@ int avs_rollout_grad_dev(avs_ctx* ctx, int N, int T, int substeps, const double*
     return AVS_OK;
 }
 
+int avs_rollout_grad_dev(avs_ctx* ctx, int N, int T, int substeps, const double* d_x0, const double* d_ctrl, const double* d_gt, double explode_thresh,
+                         int explode_mode, double* d_loss, double* d_reduced, double* d_grad_live) {
+    return rollout_grad_impl(ctx, N, T, substeps, d_x0, d_ctrl, d_gt, explode_thresh, explode_mode, d_loss, d_reduced, d_grad_live, nullptr);
+}
+
 // scatter [104][N] live gradients into the reference's [416][N] layout (rows 104..415 are zero)
 int avs_rollout_grad(avs_ctx* ctx, int N, int T, int substeps, const double* x0, const double* ctrl, const double* gt, double explode_thresh,
                      int explode_mode, double* loss, double* reduced, double* grad_per_sample) {
@@ -379,9 +397,8 @@ int avs_rollout_grad(avs_ctx* ctx, int N, int T, int substeps, const double* x0,
     CK(ctx->loss.reserve(n * 8)); CK(ctx->gps.reserve((size_t)kNumLive * n * 8)); CK(ctx->reduced.reserve(AVS_REDUCED_LEN * 8));
     CK(cudaMemcpyAsync(ctx->in_x0.p, x0, b_x0, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->in_ctrl.p, ctrl, b_ctrl, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->in_gt.p, gt, b_gt, cudaMemcpyHostToDevice, ctx->stream));
-    int rc = avs_rollout_grad_dev(ctx, N, T, substeps, ctx->in_x0.as<double>(), ctx->in_ctrl.as<double>(), ctx->in_gt.as<double>(), explode_thresh,
-                                  explode_mode, ctx->loss.as<double>(), ctx->reduced.as<double>(), ctx->gps.as<double>());
+    int rc = rollout_grad_impl(ctx, N, T, substeps, ctx->in_x0.as<double>(), ctx->in_ctrl.as<double>(), ctx->in_gt.as<double>(), explode_thresh,
+                               explode_mode, ctx->loss.as<double>(), ctx->reduced.as<double>(), ctx->gps.as<double>(), gt);
     if (rc) return rc;
     if (loss) CK(cudaMemcpyAsync(loss, ctx->loss.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (reduced) CK(cudaMemcpyAsync(reduced, ctx->reduced.p, AVS_REDUCED_LEN * 8, cudaMemcpyDeviceToHost, ctx->stream));
