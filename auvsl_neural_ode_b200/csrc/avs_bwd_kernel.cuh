@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd_kernel(const __grid_c
         };
         // the stream starts at the final-state record; its (non-existent) activation record is one past the last stage
         CkptStreamAsync<kBwdBlock> st{a.ckpt + ((size_t)nrec * a.Nc + n) * kCkRows, (size_t)a.Nc * kCkRows, nrec, 39, 53, 0,
-                                      a.act + ((size_t)nrec * 4 * a.Nc + (size_t)4 * n + lane0) * kActLen, (size_t)4 * a.Nc * kActLen, 67};
+                                      a.act + (size_t)nrec * act_stage_doubles(a.Nc) + act_lane_offset(gid), act_stage_doubles(a.Nc), 67};
         st.init();
         rollout_bwd_body(a, n, loss, scratch_col<kBwdBlock>(0), st, mk_odeb);
         if (writer) a.loss[n] = loss;

@@ -333,7 +333,7 @@ static int rollout_grad_impl(avs_ctx* ctx, int N, int T, int substeps, const dou
     if (!d_grad_live) { CK(ctx->gps.reserve((size_t)kNumLive * n * 8)); d_grad_live = ctx->gps.as<double>(); }
     // reverse-sweep buffers: (S*4 + 1) state records of 14 doubles + S*4 x 4 wheels activation records of 20 doubles per vehicle; process the batch in chunks if it does not fit the budget
     const size_t per_vehicle_ck = ((size_t)(T - 1) * substeps * 4 + 1) * kCkRows * 8;
-    const size_t per_vehicle_act = (size_t)(T - 1) * substeps * 4 * kActLen * 4 * 8;
+    const size_t per_vehicle_act = (size_t)(T - 1) * substeps * 4 * kActLen * 4 * 8;  // + tile padding, see act_bytes below
     const size_t per_vehicle = per_vehicle_ck + per_vehicle_act;
     size_t chunk;
     if (ctx->plan_N == N && ctx->plan_per_vehicle == per_vehicle && ctx->plan_budget == ctx->ckpt_budget) {
@@ -352,7 +352,7 @@ static int rollout_grad_impl(avs_ctx* ctx, int N, int T, int substeps, const dou
     }
     if (chunk == 0) return fail(ctx, AVS_E_NOMEM, "avs_rollout_grad: the reverse-sweep buffers of one 256-vehicle chunk (%zu B) exceed the memory budget", per_vehicle * 256);
     CK(ctx->ckpt.reserve(chunk * per_vehicle_ck));
-    CK(ctx->act.reserve(chunk * per_vehicle_act));
+    CK(ctx->act.reserve((size_t)(T - 1) * substeps * 4 * act_stage_doubles(chunk) * 8));  // warp-tiled, padded to whole forward CTAs
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     for (size_t begin = 0; begin < n; begin += chunk) {
         const size_t cnt = (n - begin < chunk) ? (n - begin) : chunk;

@@ -53,7 +53,7 @@ __device__ __noinline__ void ode_fwd_stage_call(int lane0, double ul, double ur,
 #pragma unroll
     for (int c = 0; c < 13; c++) x[c] = T[c];
     if (STORE && rec) CkptSink::ckpt_store(rec, x, INV[0]);
-    ode_fwd<1, TIRE_NN, TERR, STORE>(c_mc, lane0, x, ul, ur, k, nullptr, ActOutPtr{act});
+    ode_fwd<1, TIRE_NN, TERR, STORE>(c_mc, lane0, x, ul, ur, k, nullptr, ActOutPtr{act, kActPairStride});
     const double h = kDt;
     double inv;
     if (s < 3) {
@@ -84,8 +84,11 @@ template <int TERR, int BLOCK, bool STORE> struct FusedStep {
     __device__ __forceinline__ void operator()(size_t step, double& inv_carry) const {
         const size_t NK = (size_t)a.Nc;
         double* rec = (STORE && writer) ? a.ckpt + ((step * 4) * NK + n) * kCkRows : nullptr;
-        double* act = STORE ? a.act + ((step * 4) * (4 * NK) + (size_t)4 * n + lane0) * kActLen : nullptr;
-        const size_t rec_stride = NK * kCkRows, act_stride = (size_t)4 * NK * kActLen;
+        // activation records: warp-tiled (avs_model.cuh, ActOutPtr); addressed by the thread's own global lane index, so
+        // tail lanes (which mirror the last vehicle) write into the padding of the last tile
+        const size_t act_stride = act_stage_doubles(NK);
+        double* act = STORE ? a.act + (step * 4) * act_stride + act_lane_offset((size_t)blockIdx.x * BLOCK + threadIdx.x) : nullptr;
+        const size_t rec_stride = NK * kCkRows;
 #pragma unroll 1
         for (int s = 0; s < 4; s++)
             ode_fwd_stage_call<TERR, BLOCK, STORE>(lane0, ul, ur, s, rec ? rec + (size_t)s * rec_stride : nullptr, STORE ? act + (size_t)s * act_stride : nullptr);
@@ -140,7 +143,7 @@ template <int BLOCK> __device__ __forceinline__ void act_prefetch(int slotACT, c
 #pragma unroll
     for (int i = 0; i < kActLen / 2; i++) {
         const unsigned saddr = (unsigned)__cvta_generic_to_shared(g_smem + (size_t)slotACT * BLOCK + ((size_t)i * BLOCK + threadIdx.x) * 2);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(src + 2 * i) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(src + (size_t)i * kActPairStride) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
 }

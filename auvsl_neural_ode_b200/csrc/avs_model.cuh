@@ -518,17 +518,28 @@ AVS_HD void quat_to_R_bwd(const double q[4], const double Rb[9], double qb[4]) {
 // written and read as ten 16-byte pairs (STG.128 / 16-byte cp.async).  The scaled inputs s1..s3 are cheaper to
 // recompute from the stage state than to store.
 constexpr int kActLen = 20;
-struct ActOutPtr {  // contiguous record in (global / host) memory, 16-byte aligned
+// Record in (global / host) memory as ten 16-byte pairs, pair i at p + i * pstride doubles.  pstride = 2: one
+// contiguous 160-byte record (host harness).  The CUDA kernels use pstride = 64: the records of the 32 lanes of a warp
+// are interleaved pair by pair ("warp tile", kActTile doubles), so that every 16-byte store / cp.async of a warp
+// covers one contiguous 512-byte span instead of 32 sectors 160 bytes apart.
+struct ActOutPtr {
     double* p;
+    int pstride = 2;
     AVS_HD void store2(int i, double a, double b) const {
 #if defined(__CUDA_ARCH__)
-        *reinterpret_cast<double2*>(p + 2 * i) = make_double2(a, b);
+        *reinterpret_cast<double2*>(p + (size_t)i * pstride) = make_double2(a, b);
 #else
-        p[2 * i] = a; p[2 * i + 1] = b;
+        p[(size_t)i * pstride] = a; p[(size_t)i * pstride + 1] = b;
 #endif
     }
-    AVS_HD ActOutPtr wheel(int k) const { return ActOutPtr{p + (size_t)k * kActLen}; }
+    AVS_HD ActOutPtr wheel(int k) const { return ActOutPtr{p + (size_t)k * kActLen, pstride}; }  // contiguous records only
 };
+constexpr int kActPairStride = 64;           // doubles between the pairs of one lane inside a warp tile
+constexpr int kActTile = kActLen * 32;       // doubles per warp tile (32 lanes x 20)
+// doubles per RK4 stage of the tiled activation buffer for nc vehicles (whole 128-thread CTAs of the forward kernel)
+AVS_HD size_t act_stage_doubles(size_t nc) { return ((4 * nc + 127) / 128) * 128 * kActLen; }
+// this lane's base inside the tiled buffer of one stage (gid = global lane index = 4 * vehicle + wheel)
+AVS_HD size_t act_lane_offset(size_t gid) { return (gid >> 5) * kActTile + (gid & 31) * 2; }
 struct ActInPtr {
     const double* p;
     AVS_HD void load2(int i, double& a, double& b) const { a = p[2 * i]; b = p[2 * i + 1]; }
