@@ -8,7 +8,7 @@ namespace avs {
 // non-inlined stage callee (168 registers, 1 % back-to-back dependent FP64); without it ptxas settles on 128 registers and a
 // more serial order (measured: forward+store 14.1 ms vs 11.5 ms at N = 4096 x T = 200); with 2 it is 12.1 ms.
 template <int TIRE, int TERR, bool STORE>
-__global__ void __launch_bounds__(kFwdBlock, (TIRE == TIRE_NN ? 3 : 1)) rollout_fwd_kernel(const __grid_constant__ RolloutArgs a) {
+__global__ void __launch_bounds__(kFwdBlock, (TIRE == TIRE_NN ? 3 : 0)) rollout_fwd_kernel(const __grid_constant__ RolloutArgs a) {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     int n = gid >> 2;
     const int lane0 = gid & 3;
