@@ -1,4 +1,5 @@
 // avs_bekker.cuh — Bekker/Wong terramechanics tire model, forward only.
+// (scalar walk = the reference's structure; the front / rear arcs normally go through the vectorised quadrature below)
 //
 // Restates BekkerDynamics::get_tire_f_ext (src/auvsl_dynamics/BekkerDynamics.cpp:31-120) and
 // BekkerTireModel::{get_features, get_forces, integrate} (src/auvsl_dynamics/BekkerTireModel.cpp:
@@ -85,6 +86,250 @@ template <int REGION> AVS_HD Bek3 bekker_integrate(const BekkerCtx& k, double up
     return sum;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Vectorised quadrature.  The reference's scalar walk is ~30 libm calls per arc on one dependent chain, with
+// branches (slow paths of pow / sin / cos) that keep ptxas from interleaving anything: measured 42 % of the FP64
+// instructions consume the result of the one before, and the code does not fit the instruction cache.  Here the 12
+// node evaluations of an arc (t0 .. t9 of the running sum, upper - dtheta, upper) are issued step by step for six
+// nodes at a time from branch-free elementary functions:
+//   * sin / cos of the nodes by rotating (sin, cos)(lower) with (sin, cos)(dtheta); the two end nodes take the
+//     context's own values, so the sigma base R (cos - cos_end) is an exact 0 there, as in the reference;
+//   * pow(b, n) = exp(n log b) with a table-free log (fdlibm kernel) and the exp of tanh_f64;
+//   * 1/j from one rsqrt (MUFU seed + two Newton steps), j = q / sqrt(q).
+// Results agree with the scalar walk to ~1e-14 relative (tests/test_device_math_cpu.py compares both with the oracle).
+// ------------------------------------------------------------------------------------------------
+AVS_HD void split_hi_lo(double x, int& hi, int& lo) {
+#if defined(__CUDA_ARCH__)
+    hi = __double2hiint(x); lo = __double2loint(x);
+#else
+    int64_t b; memcpy(&b, &x, 8); hi = (int)(b >> 32); lo = (int)(b & 0xffffffff);
+#endif
+}
+AVS_HD double join_hi_lo(int hi, int lo) {
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(hi, lo);
+#else
+    int64_t b = ((int64_t)hi << 32) | (uint32_t)lo; double x; memcpy(&x, &b, 8); return x;
+#endif
+}
+AVS_HD double rcp_seed(double d) {
+#if defined(__CUDA_ARCH__)
+    double r; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d)); return r;
+#else
+    return 1.0 / d;
+#endif
+}
+AVS_HD double rsqrt_seed(double d) {
+#if defined(__CUDA_ARCH__)
+    double r; asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d)); return r;
+#else
+    return 1.0 / sqrt(d);
+#endif
+}
+
+// W-wide natural logarithm of non-negative normal numbers (0 maps to about -709), in place.  fdlibm's kernel:
+// x = 2^k m, m in [sqrt(1/2), sqrt(2)), f = m - 1, s = f / (2 + f), log m = f - f^2/2 + s (f^2/2 + R(s^2)).
+template <int W> AVS_HD void log_vec(double* x) {
+    const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
+    const double Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01, Lg3 = 2.857142874366239149e-01,
+                 Lg4 = 2.222219843214978396e-01, Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
+                 Lg7 = 1.479819860511658591e-01;
+    double f[W], dk[W], s[W], z[W], w[W], t1[W], t2[W], h[W];
+#pragma unroll
+    for (int i = 0; i < W; i++) {
+        int hi, lo;
+        split_hi_lo(x[i], hi, lo);
+        hi += 0x3ff00000 - 0x3fe6a09e;
+        dk[i] = (double)((hi >> 20) - 0x3ff);
+        hi = (hi & 0x000fffff) + 0x3fe6a09e;
+        f[i] = join_hi_lo(hi, lo) - 1.0;
+    }
+    // s = f / (2 + f): reciprocal seed + two Newton steps + residual correction
+#pragma unroll
+    for (int i = 0; i < W; i++) h[i] = 2.0 + f[i];
+#pragma unroll
+    for (int i = 0; i < W; i++) w[i] = rcp_seed(h[i]);
+#pragma unroll
+    for (int i = 0; i < W; i++) t1[i] = fma(-h[i], w[i], 1.0);
+#pragma unroll
+    for (int i = 0; i < W; i++) t1[i] = fma(t1[i], t1[i], t1[i]);
+#pragma unroll
+    for (int i = 0; i < W; i++) w[i] = fma(w[i], t1[i], w[i]);
+#pragma unroll
+    for (int i = 0; i < W; i++) s[i] = f[i] * w[i];
+#pragma unroll
+    for (int i = 0; i < W; i++) t1[i] = fma(-h[i], s[i], f[i]);
+#pragma unroll
+    for (int i = 0; i < W; i++) s[i] = fma(t1[i], w[i], s[i]);
+#pragma unroll
+    for (int i = 0; i < W; i++) z[i] = s[i] * s[i];
+#pragma unroll
+    for (int i = 0; i < W; i++) w[i] = z[i] * z[i];
+#pragma unroll
+    for (int i = 0; i < W; i++) { t1[i] = fma(w[i], Lg6, Lg4); t2[i] = fma(w[i], Lg7, Lg5); }
+#pragma unroll
+    for (int i = 0; i < W; i++) { t1[i] = fma(w[i], t1[i], Lg2); t2[i] = fma(w[i], t2[i], Lg3); }
+#pragma unroll
+    for (int i = 0; i < W; i++) { t1[i] = w[i] * t1[i]; t2[i] = fma(w[i], t2[i], Lg1); }
+#pragma unroll
+    for (int i = 0; i < W; i++) t2[i] = fma(z[i], t2[i], t1[i]);  // R
+#pragma unroll
+    for (int i = 0; i < W; i++) h[i] = 0.5 * f[i] * f[i];
+#pragma unroll
+    for (int i = 0; i < W; i++) t1[i] = fma(s[i], h[i] + t2[i], dk[i] * LN2_LO);
+#pragma unroll
+    for (int i = 0; i < W; i++) x[i] = fma(dk[i], LN2_HI, f[i] - (h[i] - t1[i]));
+}
+
+// W-wide exp for arguments in about [-700, 700], in place (same reduction and polynomial as exp_negarg)
+template <int W> AVS_HD void exp_vec(double* x) {
+    const double L2E = 1.4426950408889634e+0, MAGIC = 6755399441055744.0;
+    const double LN2_HI = 6.93147180559945286e-01, LN2_LO = 2.31904681384629956e-17;
+    double t[W], r[W], p[W];
+#pragma unroll
+    for (int i = 0; i < W; i++) t[i] = fma(x[i], L2E, MAGIC);
+#pragma unroll
+    for (int i = 0; i < W; i++) r[i] = t[i] - MAGIC;
+#pragma unroll
+    for (int i = 0; i < W; i++) p[i] = fma(r[i], -LN2_HI, x[i]);
+#pragma unroll
+    for (int i = 0; i < W; i++) r[i] = fma(r[i], -LN2_LO, p[i]);
+#pragma unroll
+    for (int i = 0; i < W; i++) p[i] = fma(2.5110049204818658e-08, r[i], 2.763265472252779e-07);
+#define AVS_POLY_STEP(C) \
+    _Pragma("unroll") for (int i = 0; i < W; i++) p[i] = fma(p[i], r[i], C);
+    AVS_POLY_STEP(2.755724088722987e-06)
+    AVS_POLY_STEP(2.4801485441561313e-05)
+    AVS_POLY_STEP(0.00019841269890076403)
+    AVS_POLY_STEP(0.0013888888952352863)
+    AVS_POLY_STEP(0.008333333333319589)
+    AVS_POLY_STEP(0.04166666666648795)
+    AVS_POLY_STEP(0.1666666666666668)
+    AVS_POLY_STEP(0.5000000000000019)
+    AVS_POLY_STEP(1.0)
+    AVS_POLY_STEP(1.0)
+#undef AVS_POLY_STEP
+#pragma unroll
+    for (int i = 0; i < W; i++) {
+#if defined(__CUDA_ARCH__)
+        int k = __double2loint(t[i]);
+        k = min(max(k, -1000), 1000);
+        x[i] = __hiloint2double(__double2hiint(p[i]) + (k << 20), __double2loint(p[i]));
+#else
+        int64_t k = (int64_t)(t[i] - MAGIC);
+        if (k < -1000) k = -1000;
+        if (k > 1000) k = 1000;
+        x[i] = ldexp(p[i], (int)k);
+#endif
+    }
+}
+AVS_HD double pow_pos(double b, double e) {  // b >= 0; pow(0, e > 0) comes out as ~1e-246 instead of 0
+    double v[1] = {b};
+    log_vec<1>(v);
+    v[0] *= e;
+    exp_vec<1>(v);
+    return v[0];
+}
+
+// integrand values of the front (REGION 0) or rear (REGION 2) arc at W nodes with known th, sin th, cos th
+template <int REGION, int W>
+AVS_HD void bekker_nodes_vec(const BekkerCtx& k, const double* th, const double* s, const double* c, double* fx, double* fy, double* fz) {
+    static_assert(REGION == 0 || REGION == 2, "the centre arc stays on the scalar walk");
+    const double om = 1.0 - k.slip_ratio;
+    const double cos_end = (REGION == 0) ? k.cos_tf : k.cos_tr;
+    const double coef = (REGION == 0) ? k.kk : k.ku;
+    const double invK = 1.0 / k.K;
+    double sg[W], jx[W], jy[W], q[W], r[W], e[W];
+#pragma unroll
+    for (int i = 0; i < W; i++) sg[i] = k.R * (c[i] - cos_end);
+    log_vec<W>(sg);
+#pragma unroll
+    for (int i = 0; i < W; i++) sg[i] *= k.n;
+    exp_vec<W>(sg);
+#pragma unroll
+    for (int i = 0; i < W; i++) sg[i] *= coef;                                                  // sigma :18-35
+#pragma unroll
+    for (int i = 0; i < W; i++) {
+        if (REGION == 0) {
+            jx[i] = k.R * ((th[i] - k.theta_f) - om * (s[i] - k.sin_tf));                       // :37-40
+            jy[i] = k.R * om * k.tan_sa * (k.theta_f - th[i]);                                  // :51-54
+        } else {
+            jx[i] = k.R * ((2 * k.theta_c + th[i] - k.theta_f) - om * (s[i] - k.sin_tf) - 2 * k.sin_tc);  // :46-49
+            jy[i] = k.R * om * k.tan_sa * (k.theta_f - th[i] - 2 * k.theta_c + 2 * k.sin_tc);            // :59-62
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < W; i++) q[i] = fma(jy[i], jy[i], jx[i] * jx[i]);
+    // r = 1/sqrt(q): seed + two Newton steps
+#pragma unroll
+    for (int i = 0; i < W; i++) e[i] = q[i] > 1e-290 ? q[i] : 1e-290;
+#pragma unroll
+    for (int i = 0; i < W; i++) r[i] = rsqrt_seed(e[i]);
+#pragma unroll
+    for (int i = 0; i < W; i++) { const double h = 0.5 * r[i]; r[i] = fma(h, fma(-e[i] * r[i], r[i], 1.0), r[i]); }
+#pragma unroll
+    for (int i = 0; i < W; i++) { const double h = 0.5 * r[i]; r[i] = fma(h, fma(-e[i] * r[i], r[i], 1.0), r[i]); }
+    // j = q r ; j == 0 -> 1e-6 ("smart divide" :83-84), 1/j = r
+#pragma unroll
+    for (int i = 0; i < W; i++) {
+        const bool zero = (q[i] == 0.0);
+        e[i] = zero ? -1e-6 * invK : -(q[i] * r[i]) * invK;
+        r[i] = zero ? 1e6 : r[i];
+    }
+    exp_vec<W>(e);
+#pragma unroll
+    for (int i = 0; i < W; i++) {
+        const double shear = (k.c + sg[i] * k.tan_phi) * (1.0 - e[i]);
+        const double tau_x = (-jx[i] * r[i]) * shear;                                           // :80-104
+        const double tau_y = (-jy[i] * r[i]) * shear;                                           // :106-129
+        fx[i] = tau_x * c[i] - sg[i] * s[i];                                                    // Fx_eqn1/2 :146-154
+        fy[i] = tau_y;
+        fz[i] = sg[i] * c[i] + tau_x * s[i];                                                    // Fz_eqn1/2 :137-144
+    }
+}
+
+// BekkerTireModel::integrate (:163-179) of the front / rear arc with the 12 node evaluations vectorised.
+// (sin, cos) of the two bounds are passed in; degenerate arcs take the scalar walk.
+template <int REGION>
+AVS_HD Bek3 bekker_integrate_vec(const BekkerCtx& k, double upper_b, double lower_b, double sin_lo, double cos_lo, double sin_up, double cos_up) {
+    const double dtheta = (upper_b - lower_b) / 10.0;
+    if (!(dtheta > 1e-9)) return bekker_integrate<REGION>(k, upper_b, lower_b);
+    double th[12], s[12], c[12], fx[12], fy[12], fz[12];
+    th[0] = lower_b;
+#pragma unroll
+    for (int i = 1; i < 10; i++) th[i] = th[i - 1] + dtheta;  // the reference's running theta += dtheta
+    th[10] = upper_b - dtheta;
+    th[11] = upper_b;
+    double sd, cd;
+#if defined(__CUDA_ARCH__)
+    sincos(dtheta, &sd, &cd);
+#else
+    sd = sin(dtheta); cd = cos(dtheta);
+#endif
+    s[0] = sin_lo; c[0] = cos_lo;
+#pragma unroll
+    for (int i = 1; i < 10; i++) {
+        s[i] = fma(s[i - 1], cd, c[i - 1] * sd);
+        c[i] = fma(c[i - 1], cd, -s[i - 1] * sd);
+    }
+    s[11] = sin_up; c[11] = cos_up;
+    s[10] = fma(sin_up, cd, -cos_up * sd);
+    c[10] = fma(cos_up, cd, sin_up * sd);
+    bekker_nodes_vec<REGION, 6>(k, th, s, c, fx, fy, fz);
+    bekker_nodes_vec<REGION, 6>(k, th + 6, s + 6, c + 6, fx + 6, fy + 6, fz + 6);
+    Bek3 sum = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int it = 0; it < 9; it++) {
+        sum.fx += .5 * dtheta * (fx[it + 1] + fx[it]);
+        sum.fy += .5 * dtheta * (fy[it + 1] + fy[it]);
+        sum.fz += .5 * dtheta * (fz[it + 1] + fz[it]);
+    }
+    sum.fx += .5 * dtheta * (fx[11] + fx[10]);
+    sum.fy += .5 * dtheta * (fy[11] + fy[10]);
+    sum.fz += .5 * dtheta * (fz[11] + fz[10]);
+    return sum;
+}
+
 // One wheel: (contact vx, vy, wheel speed w, sinkage) -> (Fx, Fy, Fz) before the damping term
 template <int TERR>
 AVS_HD void bekker_tire_fwd(const ModelConst& mc, double cvx, double cvy, double w, double sinkage, const double cp[3], double F[3]) {
@@ -108,7 +353,7 @@ AVS_HD void bekker_tire_fwd(const ModelConst& mc, double cvx, double cvy, double
     const double vx_c = fabs(cvx) > 1e-3 ? cvx : 1e-3;
     const double wr_c = fabs(vel_x_tan) > 1e-3 ? vel_x_tan : 1e-3;
     const double slip_ratio = 1 - (vx_c / wr_c);
-    const double slip_angle = tanh(cvy / fabs(vx_c));
+    const double slip_angle = tanh_f64(cvy / fabs(vx_c));
 
     double Fx = 0.0, Fy = 0.0, Fz = 0.0;
     if (sinkage > 0.0) {  // BekkerDynamics.cpp:81
@@ -121,20 +366,24 @@ AVS_HD void bekker_tire_fwd(const ModelConst& mc, double cvx, double cvy, double
         k.tan_phi = tan(phi);
         k.n = n0 + (n1 * fabs(slip_ratio));
         k.kk = (kc / k.b) + kphi;
-        const double pgc = k.kk * pow(zr, k.n);
+        const double pgc = k.kk * pow_pos(zr, k.n);
         if (pgc < k.pg) k.ze = zr;
-        else k.ze = pow(k.pg / k.kk, 1.0 / k.n);
+        else k.ze = pow_pos(k.pg / k.kk, 1.0 / k.n);
         k.ku = k0 + (Au * k.ze);
-        const double zu = pow(k.kk / k.ku, 1.0 / k.n) * k.ze;
-        k.theta_f = acos(1 - (zr / k.R));
-        k.theta_r = -acos(1 - ((zu + zr - k.ze) / k.R));
-        k.theta_c = acos(1 - ((zr - k.ze) / k.R));
-        k.cos_tf = cos(k.theta_f); k.sin_tf = sin(k.theta_f);
-        k.cos_tr = cos(k.theta_r);
-        k.cos_tc = cos(k.theta_c); k.sin_tc = sin(k.theta_c);
+        const double zu = pow_pos(k.kk / k.ku, 1.0 / k.n) * k.ze;
+        // contact angles: theta = acos(1 - u) with u in [0, 1]; their cosines are 1 - u and their sines sqrt(u (2 - u))
+        // (the reference calls cos / sin on the acos results; identical up to rounding, five libm calls fewer)
+        const double uf = zr / k.R, ur = (zu + zr - k.ze) / k.R, uc = (zr - k.ze) / k.R;
+        k.theta_f = acos(1 - uf);
+        k.theta_r = -acos(1 - ur);
+        k.theta_c = acos(1 - uc);
+        k.cos_tf = 1 - uf; k.sin_tf = sqrt(uf * (2 - uf));
+        k.cos_tr = 1 - ur;
+        k.cos_tc = 1 - uc; k.sin_tc = sqrt(uc * (2 - uc));
+        const double sin_tr = -sqrt(ur * (2 - ur));
         const double bt_R = k.R * k.b;
-        const Bek3 If = bekker_integrate<0>(k, k.theta_f, k.theta_c);
-        const Bek3 Ir = bekker_integrate<2>(k, -k.theta_c, k.theta_r);
+        const Bek3 If = bekker_integrate_vec<0>(k, k.theta_f, k.theta_c, k.sin_tc, k.cos_tc, k.sin_tf, k.cos_tf);
+        const Bek3 Ir = bekker_integrate_vec<2>(k, -k.theta_c, k.theta_r, sin_tr, k.cos_tr, -k.sin_tc, k.cos_tc);
         Bek3 Ic = {0.0, 0.0, 0.0};
         if (k.theta_c != 0.0) Ic = bekker_integrate<1>(k, k.theta_c, -k.theta_c);
         Fx = bt_R * If.fx + bt_R * k.cos_tc * Ic.fx + bt_R * Ir.fx;                // :245-247
