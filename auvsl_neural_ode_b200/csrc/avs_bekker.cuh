@@ -90,8 +90,8 @@ template <int REGION> AVS_HD Bek3 bekker_integrate(const BekkerCtx& k, double up
 // Vectorised quadrature.  The reference's scalar walk is ~30 libm calls per arc on one dependent chain, with
 // branches (slow paths of pow / sin / cos) that keep ptxas from interleaving anything: measured 42 % of the FP64
 // instructions consume the result of the one before, and the code does not fit the instruction cache.  Here the 12
-// node evaluations of an arc (t0 .. t9 of the running sum, upper - dtheta, upper) are issued step by step for six
-// nodes at a time from branch-free elementary functions:
+// node evaluations of an arc (t0 .. t9 of the running sum, upper - dtheta, upper) are issued step by step for four
+// nodes at a time (measured best of 4 / 6 / 12) from branch-free elementary functions:
 //   * sin / cos of the nodes by rotating (sin, cos)(lower) with (sin, cos)(dtheta); the two end nodes take the
 //     context's own values, so the sigma base R (cos - cos_end) is an exact 0 there, as in the reference;
 //   * pow(b, n) = exp(n log b) with a table-free log (fdlibm kernel) and the exp of tanh_f64;
@@ -315,8 +315,9 @@ AVS_HD Bek3 bekker_integrate_vec(const BekkerCtx& k, double upper_b, double lowe
     s[11] = sin_up; c[11] = cos_up;
     s[10] = fma(sin_up, cd, -cos_up * sd);
     c[10] = fma(cos_up, cd, sin_up * sd);
-    bekker_nodes_vec<REGION, 6>(k, th, s, c, fx, fy, fz);
-    bekker_nodes_vec<REGION, 6>(k, th + 6, s + 6, c + 6, fx + 6, fy + 6, fz + 6);
+    bekker_nodes_vec<REGION, 4>(k, th, s, c, fx, fy, fz);
+    bekker_nodes_vec<REGION, 4>(k, th + 4, s + 4, c + 4, fx + 4, fy + 4, fz + 4);
+    bekker_nodes_vec<REGION, 4>(k, th + 8, s + 8, c + 8, fx + 8, fy + 8, fz + 8);
     Bek3 sum = {0.0, 0.0, 0.0};
 #pragma unroll
     for (int it = 0; it < 9; it++) {
