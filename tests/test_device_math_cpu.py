@@ -145,3 +145,31 @@ def test_grid_terrain_and_soil_vs_oracle():
     lh, gps_h = hc.rollout_grad(m, x0, ctrl, gt, 20)
     np.testing.assert_allclose(lh, lo, rtol=1e-10)
     np.testing.assert_allclose(gps_h, gps_o[:104], rtol=1e-7, atol=1e-11 * np.abs(gps_o).max())
+
+
+def test_bekker_vectorised_quadrature_vs_oracle_random_inputs():
+    """avs_bekker.cuh evaluates the front / rear arcs with its own branch-free log / exp / rsqrt and rotated sines;
+    against the oracle's scalar walk (BekkerTireModel.cpp:163-278) over random sinkage, slip and soil — including
+    soft soil, where the centre arc is active."""
+    import ctypes as C
+    rng = np.random.default_rng(1)
+    p = po.bekker_default_params()
+    worst = 0.0
+    for it in range(1500):
+        zr = 10 ** rng.uniform(-5, -1.0)
+        vx, vy, w = rng.uniform(-1, 2), rng.uniform(-0.5, 0.5), rng.uniform(-5, 12)
+        soil = p.copy()
+        if it % 3 == 1:
+            soil = p * rng.uniform(0.5, 1.5, 5)
+            soil[3] = rng.uniform(0, 0.3)
+        if it % 3 == 2:
+            soil = p * np.array([0.02, 0.02, 1, 1, 1])
+        m = hc.model(1, po.FLAT, soil)
+        F = np.zeros(3)
+        hc.lib().hc_bekker_tire(C.byref(m), C.c_double(vx), C.c_double(vy), C.c_double(w), C.c_double(zr), F.ctypes.data_as(C.POINTER(C.c_double)))
+        feat_soil = np.array([100 * soil[0], 1000 * soil[1], soil[2], max(soil[3], 0), soil[4]])  # BekkerDynamics.cpp:59-63
+        _, f = po.bekker_forces([zr, vx, vy, 0.098 * w], feat_soil)
+        fx = abs(f[0]) if (0.098 * w - vx > 0) else -abs(f[0])                                     # BekkerDynamics.cpp:93
+        ref = np.array([fx, f[1], f[2]])
+        worst = max(worst, float(np.max(np.abs(F - ref) / np.maximum(1e-6, np.abs(ref).max()))))
+    assert worst < 1e-10
