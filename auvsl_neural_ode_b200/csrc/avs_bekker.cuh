@@ -231,32 +231,40 @@ AVS_HD double pow_pos(double b, double e) {  // b >= 0; pow(0, e > 0) comes out 
     return v[0];
 }
 
-// integrand values of the front (REGION 0) or rear (REGION 2) arc at W nodes with known th, sin th, cos th
-template <int REGION, int W>
-AVS_HD void bekker_nodes_vec(const BekkerCtx& k, const double* th, const double* s, const double* c, double* fx, double* fy, double* fz) {
+// Everything a node of the front / rear arc needs, as run-time values: one routine serves both arcs.
+//   sigma = coef (R (cos th - cos_end))^n                                  (:18-35)
+//   jx = R ((th + A) - om (sin th - sin_tf) - B)                           (:37-49)   front: A = -theta_f, B = 0
+//   jy = RomT (C - th),  RomT = R om tan(slip angle)                       (:51-62)   rear: A = 2 theta_c - theta_f, B = 2 sin theta_c
+struct BekNodeParams {
+    double R, n, cos_end, coef, A, om, sin_tf, B, RomT, C, invK, c_soil, tan_phi;
+};
+constexpr int kBekNodeParams = 13;
+template <int REGION> AVS_HD BekNodeParams bekker_node_params(const BekkerCtx& k) {
     static_assert(REGION == 0 || REGION == 2, "the centre arc stays on the scalar walk");
-    const double om = 1.0 - k.slip_ratio;
-    const double cos_end = (REGION == 0) ? k.cos_tf : k.cos_tr;
-    const double coef = (REGION == 0) ? k.kk : k.ku;
-    const double invK = 1.0 / k.K;
+    BekNodeParams q;
+    q.R = k.R; q.n = k.n; q.om = 1.0 - k.slip_ratio; q.sin_tf = k.sin_tf;
+    q.RomT = k.R * q.om * k.tan_sa; q.invK = 1.0 / k.K; q.c_soil = k.c; q.tan_phi = k.tan_phi;
+    if (REGION == 0) { q.cos_end = k.cos_tf; q.coef = k.kk; q.A = -k.theta_f; q.B = 0.0; q.C = k.theta_f; }
+    else { q.cos_end = k.cos_tr; q.coef = k.ku; q.A = 2 * k.theta_c - k.theta_f; q.B = 2 * k.sin_tc; q.C = k.theta_f - 2 * k.theta_c + 2 * k.sin_tc; }
+    return q;
+}
+
+// integrand values at W nodes with known th, sin th, cos th
+template <int W>
+AVS_HD void bekker_nodes_vec(const BekNodeParams& k, const double* th, const double* s, const double* c, double* fx, double* fy, double* fz) {
     double sg[W], jx[W], jy[W], q[W], r[W], e[W];
 #pragma unroll
-    for (int i = 0; i < W; i++) sg[i] = k.R * (c[i] - cos_end);
+    for (int i = 0; i < W; i++) sg[i] = k.R * (c[i] - k.cos_end);
     log_vec<W>(sg);
 #pragma unroll
     for (int i = 0; i < W; i++) sg[i] *= k.n;
     exp_vec<W>(sg);
 #pragma unroll
-    for (int i = 0; i < W; i++) sg[i] *= coef;                                                  // sigma :18-35
+    for (int i = 0; i < W; i++) sg[i] *= k.coef;
 #pragma unroll
     for (int i = 0; i < W; i++) {
-        if (REGION == 0) {
-            jx[i] = k.R * ((th[i] - k.theta_f) - om * (s[i] - k.sin_tf));                       // :37-40
-            jy[i] = k.R * om * k.tan_sa * (k.theta_f - th[i]);                                  // :51-54
-        } else {
-            jx[i] = k.R * ((2 * k.theta_c + th[i] - k.theta_f) - om * (s[i] - k.sin_tf) - 2 * k.sin_tc);  // :46-49
-            jy[i] = k.R * om * k.tan_sa * (k.theta_f - th[i] - 2 * k.theta_c + 2 * k.sin_tc);            // :59-62
-        }
+        jx[i] = k.R * (((th[i] + k.A) - k.om * (s[i] - k.sin_tf)) - k.B);
+        jy[i] = k.RomT * (k.C - th[i]);
     }
 #pragma unroll
     for (int i = 0; i < W; i++) q[i] = fma(jy[i], jy[i], jx[i] * jx[i]);
@@ -273,13 +281,13 @@ AVS_HD void bekker_nodes_vec(const BekkerCtx& k, const double* th, const double*
 #pragma unroll
     for (int i = 0; i < W; i++) {
         const bool zero = (q[i] == 0.0);
-        e[i] = zero ? -1e-6 * invK : -(q[i] * r[i]) * invK;
+        e[i] = zero ? -1e-6 * k.invK : -(q[i] * r[i]) * k.invK;
         r[i] = zero ? 1e6 : r[i];
     }
     exp_vec<W>(e);
 #pragma unroll
     for (int i = 0; i < W; i++) {
-        const double shear = (k.c + sg[i] * k.tan_phi) * (1.0 - e[i]);
+        const double shear = (k.c_soil + sg[i] * k.tan_phi) * (1.0 - e[i]);
         const double tau_x = (-jx[i] * r[i]) * shear;                                           // :80-104
         const double tau_y = (-jy[i] * r[i]) * shear;                                           // :106-129
         fx[i] = tau_x * c[i] - sg[i] * s[i];                                                    // Fx_eqn1/2 :146-154
@@ -288,10 +296,21 @@ AVS_HD void bekker_nodes_vec(const BekkerCtx& k, const double* th, const double*
     }
 }
 
+// How the 12 nodes of an arc are evaluated: inline, four at a time (host harness, single-ODE kernels).  The rollout kernel
+// substitutes a policy that runs the same routine as ONE non-inlined function called three times per arc, so that the hot
+// quadrature code is ~350 instructions that stay in the instruction cache instead of six unrolled copies (avs_dev.cuh).
+struct BekNodesInline {
+    AVS_HD void operator()(const BekNodeParams& q, const double* th, const double* s, const double* c, double* fx, double* fy, double* fz) const {
+        bekker_nodes_vec<4>(q, th, s, c, fx, fy, fz);
+        bekker_nodes_vec<4>(q, th + 4, s + 4, c + 4, fx + 4, fy + 4, fz + 4);
+        bekker_nodes_vec<4>(q, th + 8, s + 8, c + 8, fx + 8, fy + 8, fz + 8);
+    }
+};
+
 // BekkerTireModel::integrate (:163-179) of the front / rear arc with the 12 node evaluations vectorised.
 // (sin, cos) of the two bounds are passed in; degenerate arcs take the scalar walk.
-template <int REGION>
-AVS_HD Bek3 bekker_integrate_vec(const BekkerCtx& k, double upper_b, double lower_b, double sin_lo, double cos_lo, double sin_up, double cos_up) {
+template <int REGION, class Eval>
+AVS_HD Bek3 bekker_integrate_vec(const BekkerCtx& k, double upper_b, double lower_b, double sin_lo, double cos_lo, double sin_up, double cos_up, const Eval& eval) {
     const double dtheta = (upper_b - lower_b) / 10.0;
     if (!(dtheta > 1e-9)) return bekker_integrate<REGION>(k, upper_b, lower_b);
     double th[12], s[12], c[12], fx[12], fy[12], fz[12];
@@ -315,9 +334,7 @@ AVS_HD Bek3 bekker_integrate_vec(const BekkerCtx& k, double upper_b, double lowe
     s[11] = sin_up; c[11] = cos_up;
     s[10] = fma(sin_up, cd, -cos_up * sd);
     c[10] = fma(cos_up, cd, sin_up * sd);
-    bekker_nodes_vec<REGION, 4>(k, th, s, c, fx, fy, fz);
-    bekker_nodes_vec<REGION, 4>(k, th + 4, s + 4, c + 4, fx + 4, fy + 4, fz + 4);
-    bekker_nodes_vec<REGION, 4>(k, th + 8, s + 8, c + 8, fx + 8, fy + 8, fz + 8);
+    eval(bekker_node_params<REGION>(k), th, s, c, fx, fy, fz);
     Bek3 sum = {0.0, 0.0, 0.0};
 #pragma unroll
     for (int it = 0; it < 9; it++) {
@@ -332,8 +349,8 @@ AVS_HD Bek3 bekker_integrate_vec(const BekkerCtx& k, double upper_b, double lowe
 }
 
 // One wheel: (contact vx, vy, wheel speed w, sinkage) -> (Fx, Fy, Fz) before the damping term
-template <int TERR>
-AVS_HD void bekker_tire_fwd(const ModelConst& mc, double cvx, double cvy, double w, double sinkage, const double cp[3], double F[3]) {
+template <int TERR, class Eval = BekNodesInline>
+AVS_HD void bekker_tire_fwd(const ModelConst& mc, double cvx, double cvy, double w, double sinkage, const double cp[3], double F[3], const Eval& eval = Eval()) {
     // soil parameters: global 5-vector (BekkerDynamics.cpp:12-21, 59-63) or per-contact-point grids (extension)
     double p0 = mc.bek[0], p1 = mc.bek[1], p2 = mc.bek[2], p3 = mc.bek[3], p4 = mc.bek[4];
     const int terr_kind = (TERR == TERR_DYN) ? mc.terr_kind : TERR;
@@ -383,8 +400,8 @@ AVS_HD void bekker_tire_fwd(const ModelConst& mc, double cvx, double cvy, double
         k.cos_tc = 1 - uc; k.sin_tc = sqrt(uc * (2 - uc));
         const double sin_tr = -sqrt(ur * (2 - ur));
         const double bt_R = k.R * k.b;
-        const Bek3 If = bekker_integrate_vec<0>(k, k.theta_f, k.theta_c, k.sin_tc, k.cos_tc, k.sin_tf, k.cos_tf);
-        const Bek3 Ir = bekker_integrate_vec<2>(k, -k.theta_c, k.theta_r, sin_tr, k.cos_tr, -k.sin_tc, k.cos_tc);
+        const Bek3 If = bekker_integrate_vec<0>(k, k.theta_f, k.theta_c, k.sin_tc, k.cos_tc, k.sin_tf, k.cos_tf, eval);
+        const Bek3 Ir = bekker_integrate_vec<2>(k, -k.theta_c, k.theta_r, sin_tr, k.cos_tr, -k.sin_tc, k.cos_tc, eval);
         Bek3 Ic = {0.0, 0.0, 0.0};
         if (k.theta_c != 0.0) Ic = bekker_integrate<1>(k, k.theta_c, -k.theta_c);
         Fx = bt_R * If.fx + bt_R * k.cos_tc * Ic.fx + bt_R * Ir.fx;                // :245-247

@@ -22,6 +22,39 @@ template <int BLOCK> __device__ __forceinline__ Scratch<BLOCK> scratch_col(int s
     return Scratch<BLOCK>{g_smem + slot * BLOCK + threadIdx.x};
 }
 
+// ---- Bekker quadrature nodes as ONE non-inlined routine (four nodes per call, both arcs) ---------------------------------
+// Hand-off through kBekScratch scratch columns that follow the kFwdScratch forward columns:
+//   node parameters 0..12 | th 13..16 | sin 17..20 | cos 21..24 | fx 25..28 | fy 29..32 | fz 33..36
+constexpr int kBekScratch = 37;
+template <int BLOCK> __device__ __noinline__ void bekker_nodes4_call(int slot) {
+    const Scratch<BLOCK> S = scratch_col<BLOCK>(slot);
+    BekNodeParams q;
+    q.R = S[0]; q.n = S[1]; q.cos_end = S[2]; q.coef = S[3]; q.A = S[4]; q.om = S[5]; q.sin_tf = S[6]; q.B = S[7]; q.RomT = S[8]; q.C = S[9];
+    q.invK = S[10]; q.c_soil = S[11]; q.tan_phi = S[12];
+    double th[4], s[4], c[4], fx[4], fy[4], fz[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { th[i] = S[13 + i]; s[i] = S[17 + i]; c[i] = S[21 + i]; }
+    bekker_nodes_vec<4>(q, th, s, c, fx, fy, fz);
+#pragma unroll
+    for (int i = 0; i < 4; i++) { S[25 + i] = fx[i]; S[29 + i] = fy[i]; S[33 + i] = fz[i]; }
+}
+template <int BLOCK> struct BekNodesCall {
+    int slot;
+    __device__ __forceinline__ void operator()(const BekNodeParams& q, const double* th, const double* s, const double* c, double* fx, double* fy, double* fz) const {
+        const Scratch<BLOCK> S = scratch_col<BLOCK>(slot);
+        S[0] = q.R; S[1] = q.n; S[2] = q.cos_end; S[3] = q.coef; S[4] = q.A; S[5] = q.om; S[6] = q.sin_tf; S[7] = q.B; S[8] = q.RomT; S[9] = q.C;
+        S[10] = q.invK; S[11] = q.c_soil; S[12] = q.tan_phi;
+#pragma unroll
+        for (int g = 0; g < 3; g++) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) { S[13 + i] = th[4 * g + i]; S[17 + i] = s[4 * g + i]; S[21 + i] = c[4 * g + i]; }
+            bekker_nodes4_call<BLOCK>(slot);
+#pragma unroll
+            for (int i = 0; i < 4; i++) { fx[4 * g + i] = S[25 + i]; fy[4 * g + i] = S[29 + i]; fz[4 * g + i] = S[33 + i]; }
+        }
+    }
+};
+
 // K = f(T):  T, K = scratch slots (13 columns each); act (STORE_ACT) = this lane's activation record of the stage
 template <int TIRE, int TERR, int BLOCK, bool STORE_ACT>
 __device__ __noinline__ void ode_fwd_call(int lane0, int slotT, int slotK, double ul, double ur, double* act) {
@@ -29,7 +62,8 @@ __device__ __noinline__ void ode_fwd_call(int lane0, int slotT, int slotK, doubl
     double X[13], Xd[13];
 #pragma unroll
     for (int c = 0; c < 13; c++) X[c] = T[c];
-    ode_fwd<1, TIRE, TERR, STORE_ACT>(c_mc, lane0, X, ul, ur, Xd, nullptr, ActOutPtr{act});
+    if (TIRE == TIRE_BEKKER) ode_fwd<1, TIRE, TERR, STORE_ACT, BekNodesCall<BLOCK>>(c_mc, lane0, X, ul, ur, Xd, nullptr, ActOutPtr{act}, BekNodesCall<BLOCK>{kFwdScratch});
+    else ode_fwd<1, TIRE, TERR, STORE_ACT>(c_mc, lane0, X, ul, ur, Xd, nullptr, ActOutPtr{act});
 #pragma unroll
     for (int c = 0; c < 13; c++) K[c] = Xd[c];
 }

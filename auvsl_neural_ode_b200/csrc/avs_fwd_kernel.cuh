@@ -40,7 +40,7 @@ template <int TIRE, int TERR, bool STORE>
 static cudaError_t launch_fwd_t(const ModelConst& mc, const double* d_live, const RolloutArgs& a, cudaStream_t s) {
     const long long threads = (long long)a.Nc * 4;
     const int grid = (int)((threads + kFwdBlock - 1) / kFwdBlock);
-    const size_t smem = (size_t)kFwdScratch * kFwdBlock * sizeof(double);
+    const size_t smem = (size_t)(kFwdScratch + (TIRE == TIRE_BEKKER ? kBekScratch : 0)) * kFwdBlock * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(rollout_fwd_kernel<TIRE, TERR, STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     e = upload_model(mc, d_live, s);

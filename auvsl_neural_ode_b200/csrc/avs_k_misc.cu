@@ -77,7 +77,7 @@ cudaError_t launch_ode(int tire, const ModelConst& mc, const double* d_live, int
 cudaError_t launch_settle(int tire, const ModelConst& mc, const double* d_live, double* st, cudaStream_t s) {
     cudaError_t e = upload_model(mc, d_live, s);
     if (e != cudaSuccess) return e;
-    const size_t smem = kFwdScratch * 32 * sizeof(double);
+    const size_t smem = (kFwdScratch + kBekScratch) * 32 * sizeof(double);
     if (tire == TIRE_NN) settle_kernel<TIRE_NN><<<1, 32, smem, s>>>(st);
     else settle_kernel<TIRE_BEKKER><<<1, 32, smem, s>>>(st);
     return cudaGetLastError();

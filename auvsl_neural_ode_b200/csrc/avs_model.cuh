@@ -820,9 +820,9 @@ AVS_HD void wheel_sign(int i, double& tx, double& ty) {
 //   both are equal (VehicleSystem.cpp:132-133), so rollouts pass nullptr.
 //   act_out (STORE_ACT, NN only) = activation record of this thread's first wheel; the records of its WPT
 //   wheels are consecutive (kActLen doubles each)
-template <int WPT, int TIRE, int TERR, bool STORE_ACT = false>
+template <int WPT, int TIRE, int TERR, bool STORE_ACT = false, class BekEval = BekNodesInline>
 AVS_HD void ode_fwd(const ModelConst& mc, int lane0, const double X[13], double ul, double ur, double Xd[13], const double* ws = nullptr,
-                    ActOutPtr act_out = ActOutPtr{nullptr}) {
+                    ActOutPtr act_out = ActOutPtr{nullptr}, const BekEval& bek_eval = BekEval()) {
     double R[9];
     quat_to_R(X, R);
     double S[6] = {0, 0, 0, 0, 0, 0};
@@ -841,7 +841,7 @@ AVS_HD void ode_fwd(const ModelConst& mc, int lane0, const double X[13], double 
             F[2] = fma(kNNDamp, cv[2], F[2]);
             if (STORE_ACT) act_store(act.nn, dax, day, act_out.wheel(k));
         } else {
-            bekker_tire_fwd<TERR>(mc, cv[0], cv[1], wsp, sink, cp, F);
+            bekker_tire_fwd<TERR>(mc, cv[0], cv[1], wsp, sink, cp, F, bek_eval);
             F[2] = fma(kBekkerDamp, cv[2], F[2]);
         }
         wheel_aba_fwd(tx, ty, X, qd, F, C, act);
