@@ -68,15 +68,184 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd_kernel(const __grid_c
     }
 }
 
+// ---- split tire adjoint ------------------------------------------------------------------------------------------------
+// Same two roles, different cut: the producer's state chain uses the xy-net Jacobian the consumer formed a stage ahead
+// (3x3 worth of FMAs instead of the layered back-propagation, 5 staged values instead of 37, no activation traffic), the
+// consumer owns the activation stream (own cp.async ring, three tiles deep), forms J, runs the layered back-propagation for
+// the weight gradient and accumulates the outer products.
+// scratch columns: LAM 0 | YB 13 | KB 26 | record A 39 | record B 53 | activation tiles 67 (3 x kActLen) | J ring | F ring
+constexpr int kB2SlotT = 67, kB2SlotJ = kB2SlotT + 3 * kActLen, kB2SlotF = kB2SlotJ + 2 * kJLen, kB2Slots = kB2SlotF + 2 * kFLen;
+
+template <int TERR>
+__global__ void __launch_bounds__(kBwdThreads) rollout_bwd2_kernel(const __grid_constant__ RolloutArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int gid = blockIdx.x * kBwdBlock + lane;
+    int n = gid >> 2;
+    const int lane0 = gid & 3;
+    const bool valid = n < a.Nc;
+    if (!valid) n = a.Nc - 1;
+    const bool writer = valid && lane0 == 0;
+    const long nrec = (long)(a.T - 1) * a.substeps * 4;
+    if (threadIdx.x < kBwdBlock) {
+        // ---------------- producer warp: state adjoint
+        double loss;
+        int stage_counter = 0;
+        auto mk_odeb = [lane0, &stage_counter](double ul, double ur) {
+            return OdeBwdCall2<TERR, kBwdBlock>{lane0, 39, 53, 0, kB2SlotJ, kB2SlotF, ul, ur, &stage_counter};
+        };
+        CkptStreamRec<kBwdBlock> st{a.ckpt + ((size_t)nrec * a.Nc + n) * kCkRows, (size_t)a.Nc * kCkRows, nrec, 39, 53, 0};
+        st.init();
+        rollout_bwd_body(a, n, loss, scratch_col<kBwdBlock>(0), st, mk_odeb);
+        if (writer) a.loss[n] = loss;
+    } else {
+        // ---------------- consumer warp: activation stream, Jacobians one stage ahead, weight gradient
+        double g[kNumLive];
+#pragma unroll
+        for (int k = 0; k < kNumLive; k++) g[k] = 0.0;
+        const size_t astride = act_stage_doubles(a.Nc);
+        const double* act_last = a.act + (size_t)(nrec - 1) * astride + act_lane_offset(gid);  // reverse stage 0 = last forward stage
+        double* const tiles = g_smem + (size_t)kB2SlotT * kBwdBlock + (size_t)lane * 2;
+        double* const jring = g_smem + (size_t)kB2SlotJ * kBwdBlock + (size_t)lane * 2;
+        const double* const fring = g_smem + (size_t)kB2SlotF * kBwdBlock + lane;
+        auto tile_of = [tiles](int t) { return tiles + (size_t)t * kActLen * kBwdBlock; };
+        auto prefetch = [&](long j, int t) {  // activation record of reverse stage j -> tile t
+            if (j < nrec) {
+                const double* src = act_last - (size_t)j * astride;
+                double* dst = tile_of(t);
+#pragma unroll
+                for (int i = 0; i < kActLen / 2; i++) {
+                    const unsigned saddr = (unsigned)__cvta_generic_to_shared(dst + (size_t)i * kBwdBlock * 2);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(src + (size_t)i * kActPairStride) : "memory");
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        // The accumulators take 208 of the 255 registers, so both consumer routines stream the activations from the tile
+        // (one 16-byte pair at a time) instead of holding them, and work one output row / one layer at a time.
+        auto publish_jac = [&](long j, int t) {  // J of reverse stage j from tile t -> J ring, then signal
+            const ActInSmem<kBwdBlock> rec{tile_of(t)};
+            double jr[2][2];
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                double v[8];
+#pragma unroll
+                for (int jj = 0; jj < 4; jj++) {
+                    double ha, hb;
+                    rec.load2(4 + jj, ha, hb);  // h2[2jj], h2[2jj+1]
+                    const double ua = fma(-ha, ha, 1.0) * c_mc.W4[r][2 * jj], ub = fma(-hb, hb, 1.0) * c_mc.W4[r][2 * jj + 1];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) v[k] = (jj == 0) ? c_mc.W2[0][k] * ua : fma(c_mc.W2[2 * jj][k], ua, v[k]);
+#pragma unroll
+                    for (int k = 0; k < 8; k++) v[k] = fma(c_mc.W2[2 * jj + 1][k], ub, v[k]);
+                }
+                double a0 = 0.0, a2 = 0.0, b0 = 0.0, b2 = 0.0;
+#pragma unroll
+                for (int kk = 0; kk < 4; kk++) {
+                    double ha, hb;
+                    rec.load2(kk, ha, hb);  // h0[2kk], h0[2kk+1]
+                    const double wa = v[2 * kk] * fma(-ha, ha, 1.0), wb = v[2 * kk + 1] * fma(-hb, hb, 1.0);
+                    a0 = fma(c_mc.W0[2 * kk][0], wa, a0); a2 = fma(c_mc.W0[2 * kk][2], wa, a2);
+                    b0 = fma(c_mc.W0[2 * kk + 1][0], wb, b0); b2 = fma(c_mc.W0[2 * kk + 1][2], wb, b2);
+                }
+                const double os = (r == 0) ? kOutStd0 : kOutStd1;
+                jr[r][0] = -(a0 + b0) * (os / kInStd1);
+                jr[r][1] = (a2 + b2) * (os / kInStd3);
+            }
+            double dzg, pad, dax, day;
+            rec.load2(8, dzg, pad);
+            rec.load2(9, dax, day);
+            double* dst = jring + (size_t)(j & 1) * kJLen * kBwdBlock;
+            *reinterpret_cast<double2*>(dst) = make_double2(jr[0][0], jr[1][0]);                  // jxx jyx
+            *reinterpret_cast<double2*>(dst + 2 * kBwdBlock) = make_double2(jr[0][1], jr[1][1]);  // jxy jyy
+            *reinterpret_cast<double2*>(dst + 4 * kBwdBlock) = make_double2(dzg, 0.0);
+            *reinterpret_cast<double2*>(dst + 6 * kBwdBlock) = make_double2(dax, day);
+            bar_arrive64(kBarEmpty + (int)(j & 1));
+        };
+        prefetch(0, 0);
+        prefetch(1, 1);
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        publish_jac(0, 0);
+        int t0 = 0, t1 = 1, t2 = 2;  // tiles of reverse stages j, j+1, j+2
+#pragma unroll 1
+        for (long j = 0; j < nrec; j++) {
+            prefetch(j + 2, t2);
+            if (j + 1 < nrec) publish_jac(j + 1, t1);
+            const int q = (int)(j & 1);
+            bar_sync64(kBarFull + q);
+            const double* f = fring + (size_t)q * kFLen * kBwdBlock;
+            const double fxb = f[0], fyb = f[kBwdBlock], s1 = f[2 * kBwdBlock], s2 = f[3 * kBwdBlock], s3 = f[4 * kBwdBlock];
+            {
+                const ActInSmem<kBwdBlock> rec{tile_of(t0)};
+                const double o0 = fxb * kOutStd0, o1 = fyb * kOutStd1;
+                // layer 4: dW4 += o (x) h2 ; delta2 = (1 - h2^2) . W4^T o
+                double d2[8];
+#pragma unroll
+                for (int jj = 0; jj < 4; jj++) {
+                    double ha, hb;
+                    rec.load2(4 + jj, ha, hb);
+                    g[kOffW4 + 2 * jj] = fma(o0, ha, g[kOffW4 + 2 * jj]); g[kOffW4 + 2 * jj + 1] = fma(o0, hb, g[kOffW4 + 2 * jj + 1]);
+                    g[kOffW4 + 8 + 2 * jj] = fma(o1, ha, g[kOffW4 + 8 + 2 * jj]); g[kOffW4 + 8 + 2 * jj + 1] = fma(o1, hb, g[kOffW4 + 8 + 2 * jj + 1]);
+                    d2[2 * jj] = fma(c_mc.W4[1][2 * jj], o1, c_mc.W4[0][2 * jj] * o0) * fma(-ha, ha, 1.0);
+                    d2[2 * jj + 1] = fma(c_mc.W4[1][2 * jj + 1], o1, c_mc.W4[0][2 * jj + 1] * o0) * fma(-hb, hb, 1.0);
+                }
+                // layer 2: dW2 += delta2 (x) h0 ; delta0 = (1 - h0^2) . W2^T delta2   (h0 streamed pair by pair)
+                double d0[8];
+#pragma unroll
+                for (int kk = 0; kk < 4; kk++) {
+                    double ha, hb;
+                    rec.load2(kk, ha, hb);
+                    double sa = c_mc.W2[0][2 * kk] * d2[0], sb = c_mc.W2[0][2 * kk + 1] * d2[0];
+                    g[kOffW2 + 2 * kk] = fma(d2[0], ha, g[kOffW2 + 2 * kk]); g[kOffW2 + 2 * kk + 1] = fma(d2[0], hb, g[kOffW2 + 2 * kk + 1]);
+#pragma unroll
+                    for (int jx = 1; jx < 8; jx++) {
+                        sa = fma(c_mc.W2[jx][2 * kk], d2[jx], sa); sb = fma(c_mc.W2[jx][2 * kk + 1], d2[jx], sb);
+                        g[kOffW2 + jx * 8 + 2 * kk] = fma(d2[jx], ha, g[kOffW2 + jx * 8 + 2 * kk]);
+                        g[kOffW2 + jx * 8 + 2 * kk + 1] = fma(d2[jx], hb, g[kOffW2 + jx * 8 + 2 * kk + 1]);
+                    }
+                    d0[2 * kk] = sa * fma(-ha, ha, 1.0);
+                    d0[2 * kk + 1] = sb * fma(-hb, hb, 1.0);
+                }
+                // layer 0: dW0 += delta0 (x) (s1, s2, s3)
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    g[kOffW0 + k * 3 + 0] = fma(d0[k], s1, g[kOffW0 + k * 3 + 0]);
+                    g[kOffW0 + k * 3 + 1] = fma(d0[k], s2, g[kOffW0 + k * 3 + 1]);
+                    g[kOffW0 + k * 3 + 2] = fma(d0[k], s3, g[kOffW0 + k * 3 + 2]);
+                }
+            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            const int tt = t0; t0 = t1; t1 = t2; t2 = tt;
+        }
+#pragma unroll
+        for (int k = 0; k < kNumLive; k++) {
+            const double v = Group<1>::sum(g[k]);
+            if (writer) a.gps[(size_t)k * a.N + n] = v;
+        }
+    }
+}
+
+#ifndef AVS_BWD_SPLIT
+#define AVS_BWD_SPLIT 1
+#endif
+
 template <int TERR> static cudaError_t launch_bwd_t(const ModelConst& mc, const double* d_live, const RolloutArgs& a, cudaStream_t s) {
     const long long threads = (long long)a.Nc * 4;
     const int grid = (int)((threads + kBwdBlock - 1) / kBwdBlock);
+#if AVS_BWD_SPLIT
+    const size_t smem = (size_t)kB2Slots * kBwdBlock * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(rollout_bwd2_kernel<TERR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#else
     const size_t smem = (size_t)(kBwdScratch + 2 * kGradOps) * kBwdBlock * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(rollout_bwd_kernel<TERR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#endif
     if (e != cudaSuccess) return e;
     e = upload_model(mc, d_live, s);
     if (e != cudaSuccess) return e;
+#if AVS_BWD_SPLIT
+    rollout_bwd2_kernel<TERR><<<grid, kBwdThreads, smem, s>>>(a);
+#else
     rollout_bwd_kernel<TERR><<<grid, kBwdThreads, smem, s>>>(a);
+#endif
     return cudaGetLastError();
 }
 

@@ -210,6 +210,92 @@ template <int TERR, int BLOCK> struct OdeBwdCall {
     }
 };
 
+// ---- reverse kernel, split tire adjoint (rollout_bwd2_kernel) ---------------------------------------------------------
+// Consumer -> producer: per lane and stage the xy-net Jacobian, the gated z derivative and the terrain gradient
+// (kJLen doubles as four 16-byte pairs: jxx jyx | jxy jyy | dzg - | dax day), formed one stage AHEAD of the producer.
+// Producer -> consumer: Fx_bar Fy_bar s1 s2 s3 (kFLen columns).  Both rings are two deep (stage parity).
+// Named barriers: kBarFull + q = "F of a parity-q stage is staged" (producer arrives, consumer syncs),
+//                 kBarEmpty + q = "J of a parity-q stage is ready" (consumer arrives, producer syncs).  Because the consumer
+// publishes J of stage i+1 only after it has consumed F of stage i-1, and the producer stages F of stage i only after it has
+// read J of stage i, those two hand-shakes also protect the reuse of both rings.
+constexpr int kJLen = 8, kFLen = 5;
+template <int BLOCK> struct JInSmem {
+    const double* ring0;  // pair 0 of this lane in J buffer 0
+    int count;
+    __device__ __forceinline__ void get(int, TireJac& J, double& dzg, double& dax, double& day) const {
+        const int q = count & 1;
+        bar_sync64(kBarEmpty + q);
+        const double* b = ring0 + (size_t)q * kJLen * BLOCK;
+        const double2 p0 = *reinterpret_cast<const double2*>(b), p1 = *reinterpret_cast<const double2*>(b + 2 * BLOCK),
+                      p2 = *reinterpret_cast<const double2*>(b + 4 * BLOCK), p3 = *reinterpret_cast<const double2*>(b + 6 * BLOCK);
+        J.jxx = p0.x; J.jyx = p0.y; J.jxy = p1.x; J.jyy = p1.y; dzg = p2.x; dax = p3.x; day = p3.y;
+    }
+};
+template <int BLOCK> struct FOutSmem {
+    double* ring0;  // column 0 of this lane in F buffer 0
+    int count;
+    __device__ __forceinline__ void put(int, double fxb, double fyb, double s1, double s2, double s3) const {
+        const int q = count & 1;
+        double* dst = ring0 + (size_t)q * kFLen * BLOCK;
+        dst[0] = fxb; dst[BLOCK] = fyb; dst[2 * BLOCK] = s1; dst[3 * BLOCK] = s2; dst[4 * BLOCK] = s3;
+        bar_arrive64(kBarFull + q);
+    }
+};
+template <int TERR, int BLOCK>
+__device__ __noinline__ void ode_bwd_call2(int lane0, int slotXS, int slotLAM, int slotJ, int slotF, double ul, double ur, int stage_count, int s) {
+    const PairCol<BLOCK> XS = pair_col<BLOCK>(slotXS);
+    const Scratch<BLOCK> LAM = scratch_col<BLOCK>(slotLAM), YB = scratch_col<BLOCK>(slotLAM + 13), KB = scratch_col<BLOCK>(slotLAM + 26);
+    JInSmem<BLOCK> jin{g_smem + (size_t)slotJ * BLOCK + (size_t)threadIdx.x * 2, stage_count};
+    FOutSmem<BLOCK> fout{g_smem + (size_t)slotF * BLOCK + threadIdx.x, stage_count};
+    double X[13], Xb[13];
+#pragma unroll
+    for (int c = 0; c < 13; c++) X[c] = XS[c];
+    ode_bwd_nn_j<1, TERR>(c_mc, lane0, X, ul, ur, KB, Xb, jin, fout);
+    rk4_bwd_stage_update(XS, Xb, s, LAM, YB, KB);
+}
+template <int TERR, int BLOCK> struct OdeBwdCall2 {
+    int lane0, slotXA, slotXB, slotLAM, slotJ, slotF;
+    double ul, ur;
+    int* stage_counter;
+    __device__ __forceinline__ void operator()(PairCol<BLOCK> XS, Scratch<BLOCK>, Scratch<BLOCK>, Scratch<BLOCK>, int s, const double*) const {
+        const bool isA = XS.base == pair_col<BLOCK>(slotXA).base;
+        ode_bwd_call2<TERR, BLOCK>(lane0, isA ? slotXA : slotXB, slotLAM, slotJ, slotF, ul, ur, (*stage_counter)++, s);
+    }
+};
+// state-record stream only (the producer of the split kernel never touches the activation records)
+template <int BLOCK> struct CkptStreamRec {
+    const double* rec;
+    size_t rec_stride;
+    long remaining;
+    int slotA, slotB, parity;
+    __device__ __forceinline__ const double* act() const { return nullptr; }
+    __device__ __forceinline__ PairCol<BLOCK> cur() const { return pair_col<BLOCK>(parity ? slotB : slotA); }
+    __device__ __forceinline__ void prefetch_prev() {
+        if (remaining <= 0) return;
+        const double* src = rec - rec_stride;
+        const int slot = parity ? slotA : slotB;
+#pragma unroll
+        for (int i = 0; i < kCkRows / 2; i++) {
+            const unsigned saddr = (unsigned)__cvta_generic_to_shared(g_smem + (size_t)slot * BLOCK + ((size_t)i * BLOCK + threadIdx.x) * 2);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(src + 2 * i) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    __device__ __forceinline__ void init() {
+        const PairCol<BLOCK> dst = cur();
+#pragma unroll
+        for (int c = 0; c < kCkRows; c++) dst[c] = __ldg(rec + c);
+        prefetch_prev();
+    }
+    __device__ __forceinline__ void advance() {
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        parity ^= 1;
+        rec -= rec_stride;
+        remaining--;
+        prefetch_prev();
+    }
+};
+
 // Reverse record stream with one-record-ahead prefetch: while the adjoint of stage s runs (~8 k cycles), the
 // record of the stage before it is copied HBM -> this lane's shared-memory column by cp.async (LDGSTS), so the
 // HBM latency of the checkpoint stream is off the critical path of the single resident warp.

@@ -493,6 +493,65 @@ AVS_HD void tire_nn_bwd(const ModelConst& mc, const NNAct& a, const double Fbar[
     zrb = (oz * a.dz4) * (1.0 / kInStd0);
 }
 
+// ---- the tire-network adjoint split in two (reverse kernel: producer warp / consumer warp) ----------------------------
+// The state adjoint needs only  (vx_bar, vy_bar) = J^T (Fx_bar, Fy_bar)  with the 2x2 input-output Jacobian of the xy-net,
+//   J[r][c] = sum_k W0[k][c] d0[k] (sum_j W2[j][k] d2[j] W4[r][j]),   d = 1 - h^2,
+// which depends on the stored activations and the weights only — it can be formed BEFORE the adjoint of the stage runs.
+// The layered back-propagation (delta2, delta0) is needed for the weight gradient alone.  Scalings folded in:
+//   vx_bar = Fx_bar jxx + Fy_bar jyx ,  vy_bar = Fx_bar jxy + Fy_bar jyy.
+struct TireJac { double jxx, jyx, jxy, jyy; };
+AVS_HD void tire_jacobian(const ModelConst& mc, const double h0[8], const double h2[8], TireJac& J) {
+    double d0[8], d2[8], u0[8], u1[8], v0[8], v1[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { d2[k] = fma(-h2[k], h2[k], 1.0); d0[k] = fma(-h0[k], h0[k], 1.0); }
+#pragma unroll
+    for (int j = 0; j < 8; j++) { u0[j] = d2[j] * mc.W4[0][j]; u1[j] = d2[j] * mc.W4[1][j]; }
+#pragma unroll
+    for (int k = 0; k < 8; k++) { v0[k] = mc.W2[0][k] * u0[0]; v1[k] = mc.W2[0][k] * u1[0]; }
+#pragma unroll
+    for (int j = 1; j < 8; j++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) { v0[k] = fma(mc.W2[j][k], u0[j], v0[k]); v1[k] = fma(mc.W2[j][k], u1[j], v1[k]); }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) { v0[k] *= d0[k]; v1[k] *= d0[k]; }
+    double a00 = mc.W0[0][0] * v0[0], a02 = mc.W0[0][2] * v0[0], a10 = mc.W0[0][0] * v1[0], a12 = mc.W0[0][2] * v1[0];
+    double b00 = mc.W0[1][0] * v0[1], b02 = mc.W0[1][2] * v0[1], b10 = mc.W0[1][0] * v1[1], b12 = mc.W0[1][2] * v1[1];
+#pragma unroll
+    for (int k = 2; k < 8; k += 2) {
+        a00 = fma(mc.W0[k][0], v0[k], a00); a02 = fma(mc.W0[k][2], v0[k], a02); a10 = fma(mc.W0[k][0], v1[k], a10); a12 = fma(mc.W0[k][2], v1[k], a12);
+        b00 = fma(mc.W0[k + 1][0], v0[k + 1], b00); b02 = fma(mc.W0[k + 1][2], v0[k + 1], b02);
+        b10 = fma(mc.W0[k + 1][0], v1[k + 1], b10); b12 = fma(mc.W0[k + 1][2], v1[k + 1], b12);
+    }
+    // s1 = (w R - vx) / std1 (minus sign), s3 = vy / std3 ; o_r = F_bar_r * out_std_r
+    J.jxx = -(a00 + b00) * (kOutStd0 / kInStd1); J.jyx = -(a10 + b10) * (kOutStd1 / kInStd1);
+    J.jxy = (a02 + b02) * (kOutStd0 / kInStd3);  J.jyy = (a12 + b12) * (kOutStd1 / kInStd3);
+}
+// operands of the three weight-gradient outer products (order of grad_outer) from the stored activations, the two
+// output adjoints (Fx_bar, Fy_bar) and the scaled inputs — the first half of tire_nn_bwd
+AVS_HD void tire_wgrad_ops(const ModelConst& mc, const double h0[8], const double h2[8], double fxb, double fyb, double s1, double s2, double s3,
+                           double op[kGradOps]) {
+    const double o0 = fxb * kOutStd0, o1 = fyb * kOutStd1;
+    double* d2 = op + 10; double* d0 = op + 26;
+    op[0] = o0; op[1] = o1;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { op[2 + k] = h2[k]; op[18 + k] = h0[k]; }
+    op[34] = s1; op[35] = s2; op[36] = s3;
+#pragma unroll
+    for (int k = 0; k < 8; k++) d2[k] = fma(mc.W4[1][k], o1, mc.W4[0][k] * o0);
+#pragma unroll
+    for (int k = 0; k < 8; k++) d2[k] *= fma(-h2[k], h2[k], 1.0);
+#pragma unroll
+    for (int k = 0; k < 8; k++) d0[k] = mc.W2[0][k] * d2[0];
+#pragma unroll
+    for (int j = 1; j < 8; j++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) d0[k] = fma(mc.W2[j][k], d2[j], d0[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) d0[k] *= fma(-h0[k], h0[k], 1.0);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Rotation helpers (src/auvsl_dynamics/utils.cpp:45-52, 20-28)
 // ------------------------------------------------------------------------------------------------
@@ -924,6 +983,86 @@ AVS_HD void ode_bwd_nn(const ModelConst& mc, int lane0, const double X[13], doub
     }
     quat_to_R_bwd(X, Rb, Xb);
 }
+
+// The same adjoint with the tire network split off (reverse kernel): `jin.get(k, J, dzg, dax, day)` delivers, for this
+// thread's k-th wheel, the xy-net Jacobian, the gated z-branch derivative and the terrain gradient (all functions of the
+// stage's stored activations only); `fout.put(k, Fx_bar, Fy_bar, s1, s2, s3)` hands over what the weight gradient needs.
+template <int WPT, int TERR, class XD, class JIn, class FOut>
+AVS_HD void ode_bwd_nn_j(const ModelConst& mc, int lane0, const double X[13], double ul, double ur, const XD& Xdb, double Xb[13], JIn& jin, FOut& fout) {
+    double Sb[6];
+    base_bwd_S(mc, Xdb, Sb);
+    double gx[3] = {0, 0, 0}, gy[3] = {0, 0, 0}, gs[3] = {0, 0, 0};  // sum sx*cpb, sum sy*cpb, sum cpb
+    double wb[3] = {0, 0, 0}, vb[3] = {0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < WPT; k++) {
+        const int i = lane0 + k;
+        double tx, ty;
+        wheel_sign(i, tx, ty);
+        const double qd = (i & 1) ? ur : ul;
+        double Fb[3];
+        WheelAct act;
+        const double cvx = X[10] + (X[8] * kRz - X[9] * ty), cvy = X[11] + (X[9] * tx - X[7] * kRz);
+        const double s1 = (qd * kTireRadius - cvx) * (1.0 / kInStd1), s2 = qd * (1.0 / kInStd2), s3 = cvy * (1.0 / kInStd3);
+        wheel_aba_act(tx, ty, X, qd, act);
+        wheel_aba_bwd(tx, ty, qd, act, Sb, Fb, wb, vb);
+        TireJac J;
+        double dzg, dax, day;
+        jin.get(k, J, dzg, dax, day);
+        fout.put(k, Fb[0], Fb[1], s1, s2, s3);
+        double cvb[3];
+        cvb[0] = fma(Fb[1], J.jyx, Fb[0] * J.jxx);
+        cvb[1] = fma(Fb[1], J.jyy, Fb[0] * J.jxy);
+        cvb[2] = kNNDamp * Fb[2];
+        const double sinkb = (Fb[2] * kOutStd2 * dzg) * (1.0 / kInStd0);
+        // cv = v + w x r
+        vb[0] += cvb[0]; vb[1] += cvb[1]; vb[2] += cvb[2];
+        wb[0] += ty * cvb[2] - kRz * cvb[1];
+        wb[1] += kRz * cvb[0] - tx * cvb[2];
+        wb[2] += tx * cvb[1] - ty * cvb[0];
+        // sink = alt(cpx, cpy) - cpz
+        const double cpb0 = (TERR == TERR_FLAT) ? 0.0 : sinkb * dax, cpb1 = (TERR == TERR_FLAT) ? 0.0 : sinkb * day, cpb2 = -sinkb;
+        const double sx = (i & 2) ? -1.0 : 1.0, sy = (i & 1) ? -1.0 : 1.0;
+        gx[0] += sx * cpb0; gx[1] += sx * cpb1; gx[2] += sx * cpb2;
+        gy[0] += sy * cpb0; gy[1] += sy * cpb1; gy[2] += sy * cpb2;
+        gs[0] += cpb0; gs[1] += cpb1; gs[2] += cpb2;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        if (!(TERR == TERR_FLAT && c < 2)) { gx[c] = Group<WPT>::sum(gx[c]); gy[c] = Group<WPT>::sum(gy[c]); gs[c] = Group<WPT>::sum(gs[c]); }
+        wb[c] = Group<WPT>::sum(wb[c]); vb[c] = Group<WPT>::sum(vb[c]);
+    }
+    double R[9], Rb[9];
+    quat_to_R(X, R);
+    base_bwd_rest(R, X, Xdb, Sb, Xb, Rb);
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        Rb[3 * c + 0] = fma(kTx, gx[c], Rb[3 * c + 0]);
+        Rb[3 * c + 1] = fma(kTy, gy[c], Rb[3 * c + 1]);
+        Rb[3 * c + 2] = fma(kRz, gs[c], Rb[3 * c + 2]);
+        Xb[4 + c] += gs[c];
+        Xb[7 + c] += wb[c];
+        Xb[10 + c] += vb[c];
+    }
+    quat_to_R_bwd(X, Rb, Xb);
+}
+// host-side (and reference) providers: Jacobian formed on the spot from the activation records, weight gradient applied at once
+template <class Acc> struct JFromRecords {
+    const ModelConst& mc; const double* act; Acc& acc;  // act = four consecutive kActLen-double records
+    double h0[8], h2[8];
+    AVS_HD void get(int k, TireJac& J, double& dzg, double& dax, double& day) {
+        NNAct a;
+        act_load(a, dax, day, ActInPtr{act + (size_t)k * kActLen});
+        dzg = a.dz4;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { h0[i] = a.h0[i]; h2[i] = a.h2[i]; }
+        tire_jacobian(mc, h0, h2, J);
+    }
+    AVS_HD void put(int, double fxb, double fyb, double s1, double s2, double s3) {
+        double op[kGradOps];
+        tire_wgrad_ops(mc, h0, h2, fxb, fyb, s1, s2, s3, op);
+        acc.record(op);
+    }
+};
 
 // ------------------------------------------------------------------------------------------------
 // RK4 step with per-stage quaternion re-normalisation (HybridDynamics::RK4, HybridDynamics.cpp:461-502)
