@@ -1,16 +1,18 @@
-// avs_bwd_kernel.cuh — reverse-sweep (BPTT) kernel template (instantiated in avs_k_bwd_*.cu)
+// avs_bwd_kernel.cuh — reverse-sweep (BPTT) kernel templates (instantiated in avs_k_bwd_*.cu)
 //
-// rollout_bwd_kernel replaces the CppAD tape + ADFun::Reverse(1) of Trainer::trainTrajectory
-// (/root/reference/src/Trainer.cpp:607-657).  A CTA is two warps serving the same 8 vehicles x 4 wheel lanes:
-//   * producer warp — walks the checkpoint stream backwards: per RK4 stage the state record (14 doubles) and the
-//     tire-network activation record (20 doubles per wheel) arrive in shared memory by cp.async one stage ahead;
-//     it back-propagates through the base link, the ABA wheel passes, the tire network, the contact geometry /
-//     terrain gradient and the quaternion normalisations, keeping the loop-carried adjoints in shared-memory
-//     scratch columns (conflict-free: consecutive lanes -> consecutive banks);
-//   * consumer warp — holds dL/dW (104 doubles per lane) in registers and accumulates the three outer products of
-//     every stage from the 37 operands the producer stages for it (double buffer, named barriers).
-// At the end the consumer sums the 4 wheel lanes of a vehicle (shuffles) and writes gps[104][N]; the producer
-// writes loss[N].
+// They replace the CppAD tape + ADFun::Reverse(1) of Trainer::trainTrajectory (/root/reference/src/Trainer.cpp:607-657).
+// A CTA is two warps serving the same 8 vehicles x 4 wheel lanes; the loop-carried adjoints live in shared-memory scratch
+// columns (conflict-free: consecutive lanes -> consecutive banks); at the end the consumer sums the 4 wheel lanes of a
+// vehicle (shuffles) and writes gps[104][N], the producer writes loss[N].
+//
+//   rollout_bwd2_kernel (shipped, AVS_BWD_SPLIT = 1): tire adjoint split between the warps.
+//     * producer — state-record stream (cp.async one stage ahead), adjoint of the base link, the ABA wheel passes, contact
+//       geometry / terrain gradient, quaternion normalisations; through the tire network only J^T F_bar with the 2x2 Jacobian
+//       the consumer formed a stage ahead; stages 5 values per wheel for the weight gradient;
+//     * consumer — activation-record stream (own cp.async ring, three tiles), Jacobian of the NEXT stage, layered
+//       back-propagation + three outer products of the current stage into dL/dW (104 doubles per lane in registers).
+//   rollout_bwd_kernel (previous cut, AVS_BWD_SPLIT = 0): the producer does the whole tire adjoint and stages the 37 operands
+//     of the outer products; the consumer only accumulates.  14.9 ms against 12.3 ms at N = 4096 x T = 200.
 #pragma once
 #include "avs_dev.cuh"
 
