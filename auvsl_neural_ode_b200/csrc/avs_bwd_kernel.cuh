@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd_kernel(const __grid_c
 // consumer owns the activation stream (own cp.async ring, three tiles deep), forms J, runs the layered back-propagation for
 // the weight gradient and accumulates the outer products.
 // scratch columns: LAM 0 | YB 13 | KB 26 | record A 39 | record B 53 | activation tiles 67 (3 x kActLen) | J ring | F ring
-constexpr int kB2SlotT = 67, kB2SlotJ = kB2SlotT + 3 * kActLen, kB2SlotF = kB2SlotJ + 2 * kJLen, kB2Slots = kB2SlotF + 2 * kFLen;
+constexpr int kB2SlotT = 67, kB2SlotJ = kB2SlotT + 3 * kActLen, kB2SlotF = kB2SlotJ + 2 * kJLen, kB2SlotG4 = kB2SlotF + 2 * kFLen, kB2Slots = kB2SlotG4 + 16;  // + dW4 accumulators (16 per lane, as 8 pairs)
 
 template <int TERR>
 __global__ void __launch_bounds__(kBwdThreads) rollout_bwd2_kernel(const __grid_constant__ RolloutArgs a) {
@@ -101,9 +101,14 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd2_kernel(const __grid_
         if (writer) a.loss[n] = loss;
     } else {
         // ---------------- consumer warp: activation stream, Jacobians one stage ahead, weight gradient
-        double g[kNumLive];
+        double g[kOffW4];
 #pragma unroll
-        for (int k = 0; k < kNumLive; k++) g[k] = 0.0;
+        for (int k = 0; k < kOffW4; k++) g[k] = 0.0;
+        // dL/dW4 (16 of the 104) lives in shared memory as eight 16-byte pairs per lane: the 88 others take 176 registers and
+        // leave the routines below enough room not to spill
+        double* const g4 = g_smem + (size_t)kB2SlotG4 * kBwdBlock + (size_t)lane * 2;
+#pragma unroll
+        for (int i = 0; i < 8; i++) *reinterpret_cast<double2*>(g4 + (size_t)i * kBwdBlock * 2) = make_double2(0.0, 0.0);
         const size_t astride = act_stage_doubles(a.Nc);
         const double* act_last = a.act + (size_t)(nrec - 1) * astride + act_lane_offset(gid);  // reverse stage 0 = last forward stage
         double* const tiles = g_smem + (size_t)kB2SlotT * kBwdBlock + (size_t)lane * 2;
@@ -185,8 +190,14 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd2_kernel(const __grid_
                 for (int jj = 0; jj < 4; jj++) {
                     double ha, hb;
                     rec.load2(4 + jj, ha, hb);
-                    g[kOffW4 + 2 * jj] = fma(o0, ha, g[kOffW4 + 2 * jj]); g[kOffW4 + 2 * jj + 1] = fma(o0, hb, g[kOffW4 + 2 * jj + 1]);
-                    g[kOffW4 + 8 + 2 * jj] = fma(o1, ha, g[kOffW4 + 8 + 2 * jj]); g[kOffW4 + 8 + 2 * jj + 1] = fma(o1, hb, g[kOffW4 + 8 + 2 * jj + 1]);
+                    {   // pair jj = (dW4[0][2jj], dW4[0][2jj+1]), pair 4 + jj = row 1
+                        double2* q0 = reinterpret_cast<double2*>(g4 + (size_t)jj * kBwdBlock * 2);
+                        double2* q1 = reinterpret_cast<double2*>(g4 + (size_t)(4 + jj) * kBwdBlock * 2);
+                        double2 a0 = *q0, a1 = *q1;
+                        a0.x = fma(o0, ha, a0.x); a0.y = fma(o0, hb, a0.y);
+                        a1.x = fma(o1, ha, a1.x); a1.y = fma(o1, hb, a1.y);
+                        *q0 = a0; *q1 = a1;
+                    }
                     d2[2 * jj] = fma(c_mc.W4[1][2 * jj], o1, c_mc.W4[0][2 * jj] * o0) * fma(-ha, ha, 1.0);
                     d2[2 * jj + 1] = fma(c_mc.W4[1][2 * jj + 1], o1, c_mc.W4[0][2 * jj + 1] * o0) * fma(-hb, hb, 1.0);
                 }
@@ -219,9 +230,16 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd2_kernel(const __grid_
             const int tt = t0; t0 = t1; t1 = t2; t2 = tt;
         }
 #pragma unroll
-        for (int k = 0; k < kNumLive; k++) {
+        for (int k = 0; k < kOffW4; k++) {
             const double v = Group<1>::sum(g[k]);
             if (writer) a.gps[(size_t)k * a.N + n] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const double2 p = *reinterpret_cast<const double2*>(g4 + (size_t)i * kBwdBlock * 2);
+            const int k0 = kOffW4 + (i < 4 ? 2 * i : 8 + 2 * (i - 4));
+            const double vx = Group<1>::sum(p.x), vy = Group<1>::sum(p.y);
+            if (writer) { a.gps[(size_t)k0 * a.N + n] = vx; a.gps[(size_t)(k0 + 1) * a.N + n] = vy; }
         }
     }
 }
