@@ -75,8 +75,9 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd_kernel(const __grid_c
 // (3x3 worth of FMAs instead of the layered back-propagation, 5 staged values instead of 37, no activation traffic), the
 // consumer owns the activation stream (own cp.async ring, three tiles deep), forms J, runs the layered back-propagation for
 // the weight gradient and accumulates the outer products.
-// scratch columns: LAM 0 | YB 13 | KB 26 | record A 39 | record B 53 | activation tiles 67 (3 x kActLen) | J ring | F ring
-constexpr int kB2SlotT = 67, kB2SlotJ = kB2SlotT + 3 * kActLen, kB2SlotF = kB2SlotJ + 2 * kJLen, kB2SlotG4 = kB2SlotF + 2 * kFLen, kB2Slots = kB2SlotG4 + 16;  // + dW4 accumulators (16 per lane, as 8 pairs)
+// scratch columns (16-byte pairs, 14 slots per 13-vector): LAM 0 | YB 14 | KB 28 | record A 42 | record B 56 |
+// activation tiles 70 (3 x kActLen) | J ring | F ring | dW4
+constexpr int kB2SlotT = 70, kB2SlotJ = kB2SlotT + 3 * kActLen, kB2SlotF = kB2SlotJ + 2 * kJLen, kB2SlotG4 = kB2SlotF + 2 * kFLen, kB2Slots = kB2SlotG4 + 16;  // + dW4 accumulators (16 per lane, as 8 pairs)
 
 template <int TERR>
 __global__ void __launch_bounds__(kBwdThreads) rollout_bwd2_kernel(const __grid_constant__ RolloutArgs a) {
@@ -93,11 +94,11 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd2_kernel(const __grid_
         double loss;
         int stage_counter = 0;
         auto mk_odeb = [lane0, &stage_counter](double ul, double ur) {
-            return OdeBwdCall2<TERR, kBwdBlock>{lane0, 39, 53, 0, kB2SlotJ, kB2SlotF, ul, ur, &stage_counter};
+            return OdeBwdCall2<TERR, kBwdBlock>{lane0, 42, 56, 0, kB2SlotJ, kB2SlotF, ul, ur, &stage_counter};
         };
-        CkptStreamRec<kBwdBlock> st{a.ckpt + ((size_t)nrec * a.Nc + n) * kCkRows, (size_t)a.Nc * kCkRows, nrec, 39, 53, 0};
+        CkptStreamRec<kBwdBlock> st{a.ckpt + ((size_t)nrec * a.Nc + n) * kCkRows, (size_t)a.Nc * kCkRows, nrec, 42, 56, 0};
         st.init();
-        rollout_bwd_body(a, n, loss, scratch_col<kBwdBlock>(0), st, mk_odeb);
+        rollout_bwd_body(a, n, loss, pair_col<kBwdBlock>(0), st, mk_odeb);
         if (writer) a.loss[n] = loss;
     } else {
         // ---------------- consumer warp: activation stream, Jacobians one stage ahead, weight gradient

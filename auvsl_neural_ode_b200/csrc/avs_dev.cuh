@@ -159,6 +159,13 @@ template <int BLOCK> struct StagingAcc {
 template <int BLOCK> struct PairCol {
     double* base;
     __device__ __forceinline__ double& operator[](int c) const { return base[(size_t)(c >> 1) * BLOCK * 2 + (c & 1)]; }
+    __device__ __forceinline__ void load2(int i, double& a, double& b) const {
+        const double2 v = *reinterpret_cast<const double2*>(base + (size_t)i * BLOCK * 2);
+        a = v.x; b = v.y;
+    }
+    __device__ __forceinline__ void store2(int i, double a, double b) const { *reinterpret_cast<double2*>(base + (size_t)i * BLOCK * 2) = make_double2(a, b); }
+    // the 13-vector that starts c0 scalar slots later (vectors are padded to 7 pairs = 14 slots): sub(13) = next vector
+    __device__ __forceinline__ PairCol sub(int c0) const { return PairCol{base + (size_t)(c0 / 13) * 14 * BLOCK}; }
 };
 template <int BLOCK> __device__ __forceinline__ PairCol<BLOCK> pair_col(int slot) {
     return PairCol<BLOCK>{g_smem + (size_t)slot * BLOCK + (size_t)threadIdx.x * 2};
@@ -243,21 +250,43 @@ template <int BLOCK> struct FOutSmem {
 };
 template <int TERR, int BLOCK>
 __device__ __noinline__ void ode_bwd_call2(int lane0, int slotXS, int slotLAM, int slotJ, int slotF, double ul, double ur, int stage_count, int s) {
-    const PairCol<BLOCK> XS = pair_col<BLOCK>(slotXS);
-    const Scratch<BLOCK> LAM = scratch_col<BLOCK>(slotLAM), YB = scratch_col<BLOCK>(slotLAM + 13), KB = scratch_col<BLOCK>(slotLAM + 26);
+    // all loop-carried vectors are 16-byte pairs (LDS.128 / STS.128): record | LAM | YB | KB, 14 slots each
+    const PairCol<BLOCK> XS = pair_col<BLOCK>(slotXS), LAM = pair_col<BLOCK>(slotLAM), YB = pair_col<BLOCK>(slotLAM + 14), KB = pair_col<BLOCK>(slotLAM + 28);
     JInSmem<BLOCK> jin{g_smem + (size_t)slotJ * BLOCK + (size_t)threadIdx.x * 2, stage_count};
     FOutSmem<BLOCK> fout{g_smem + (size_t)slotF * BLOCK + threadIdx.x, stage_count};
-    double X[13], Xb[13];
+    double X[14], kb[14], Xb[14];
 #pragma unroll
-    for (int c = 0; c < 13; c++) X[c] = XS[c];
-    ode_bwd_nn_j<1, TERR>(c_mc, lane0, X, ul, ur, KB, Xb, jin, fout);
-    rk4_bwd_stage_update(XS, Xb, s, LAM, YB, KB);
+    for (int i = 0; i < 7; i++) { XS.load2(i, X[2 * i], X[2 * i + 1]); KB.load2(i, kb[2 * i], kb[2 * i + 1]); }
+    ode_bwd_nn_j<1, TERR>(c_mc, lane0, X, ul, ur, kb, Xb, jin, fout);
+    // rk4_bwd_stage_update on pairs
+    Xb[13] = 0.0;
+    const double h = kDt;
+    if (s > 0) {
+        renorm_bwd(X, X[13], Xb);  // stage input s = N(X + c_s k_s); X[13] = the stored inverse norm
+        const double cs = (s == 3) ? h : .5 * h;
+        const double wk = (s == 1) ? (h / 6.0) : (h / 3.0);
+#pragma unroll
+        for (int i = 0; i < 7; i++) {
+            double l0, l1, y0, y1;
+            LAM.load2(i, l0, l1);
+            YB.load2(i, y0, y1);
+            LAM.store2(i, l0 + Xb[2 * i], l1 + Xb[2 * i + 1]);
+            KB.store2(i, fma(cs, Xb[2 * i], wk * y0), fma(cs, Xb[2 * i + 1], wk * y1));
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 7; i++) {
+            double l0, l1;
+            LAM.load2(i, l0, l1);
+            LAM.store2(i, l0 + Xb[2 * i], l1 + Xb[2 * i + 1]);
+        }
+    }
 }
 template <int TERR, int BLOCK> struct OdeBwdCall2 {
     int lane0, slotXA, slotXB, slotLAM, slotJ, slotF;
     double ul, ur;
     int* stage_counter;
-    __device__ __forceinline__ void operator()(PairCol<BLOCK> XS, Scratch<BLOCK>, Scratch<BLOCK>, Scratch<BLOCK>, int s, const double*) const {
+    template <class V> __device__ __forceinline__ void operator()(PairCol<BLOCK> XS, V, V, V, int s, const double*) const {
         const bool isA = XS.base == pair_col<BLOCK>(slotXA).base;
         ode_bwd_call2<TERR, BLOCK>(lane0, isA ? slotXA : slotXB, slotLAM, slotJ, slotF, ul, ur, (*stage_counter)++, s);
     }
