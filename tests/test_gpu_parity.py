@@ -386,3 +386,45 @@ def test_reference_physical_kats_on_gpu(nn, bk):
     assert np.ptp(xl[:, 4, 2]) == pytest.approx(np.ptp(xl[:, 5, 2]), abs=1e-2)
     xl_o, _ = po.rollout_batch(po.TIRE_BEKKER, po.bekker_default_params(), po.terrain(po.FLAT), x0[:, :2], ctrl[:300, :, :2], 301, nthreads=2)
     assert rel_state_err(xl[:301, :, :2], xl_o) < 1e-7    # Bekker: value-dependent branches, 1e-7
+
+
+def test_config3_bekker_grid_full_size_properties(bk):
+    """BASELINE configs[3]: 65 536 Bekker rollouts on randomised height / soil grids over 8 GPUs = 8192 per GPU.  At that size:
+    determinism, permutation equivariance, finite states, unit quaternions, and a strided sample against the oracle."""
+    g = synth.make_grid_terrain()
+    bk.set_terrain_grid(g["height"], g["soil"], g["x0"], g["y0"], g["dx"], g["dy"])
+    N, T = 8192, 40
+    x0, ctrl, _ = synth.make_batch(N, T, z_stable=0.065)
+    ctrl = np.clip(ctrl, 0.5, 8.0)
+    _, xf = bk.rollout(x0, ctrl, T, want_list=False)
+    assert np.all(np.isfinite(xf))
+    np.testing.assert_allclose(np.sqrt((xf[:4] ** 2).sum(axis=0)), 1.0, rtol=0, atol=1e-14)
+    _, xf2 = bk.rollout(x0, ctrl, T, want_list=False)
+    assert np.array_equal(xf, xf2)
+    perm = np.random.default_rng(1).permutation(N)
+    _, xf_p = bk.rollout(x0[:, perm].copy(), ctrl[:, :, perm].copy(), T, want_list=False)
+    assert np.array_equal(xf_p, xf[:, perm])
+    idx = np.arange(0, N, 1024)
+    t = po.terrain(po.GRID, height=g["height"], soil=g["soil"], x0=g["x0"], y0=g["y0"], dx=g["dx"], dy=g["dy"])
+    _, xf_o = po.rollout_batch(po.TIRE_BEKKER, po.bekker_default_params(), t, x0[:, idx].copy(), ctrl[:, :, idx].copy(), T, want_list=False, nthreads=8)
+    assert rel_state_err(xf[:, idx], xf_o) < 1e-7  # Bekker: value-dependent branches
+    bk.set_terrain(capi.FLAT)
+
+
+def test_config4_65536_windows_per_step(nn):
+    """BASELINE configs[4] on one GPU: 65 536 windows x 200 rows per training step do not fit the record budget at once
+    (392 GB of records) and run as chunks; the first 4096 windows must come out bit-identical to a 4096-window call, the
+    reduction must be the sum of the per-sample gradients, and nothing may be dropped."""
+    nn.set_terrain(capi.FLAT)
+    nn.set_nn_params(P)
+    N, T = 65536, 200
+    x0s, ctrls, gts = synth.make_batch(4096, T)
+    reps = N // 4096
+    x0, ctrl, gt = np.tile(x0s, (1, reps)), np.tile(ctrls, (1, 1, reps)), np.tile(gts, (1, 1, reps))
+    loss, red, _ = nn.rollout_grad(x0, ctrl, gt, T, per_sample=False)
+    loss_s, red_s, _ = nn.rollout_grad(x0s, ctrls, gts, T, per_sample=False)
+    assert np.all(np.isfinite(loss)) and red[417] == N
+    for r in range(reps):
+        assert np.array_equal(loss[r * 4096:(r + 1) * 4096], loss_s)
+    np.testing.assert_allclose(red[:416], reps * red_s[:416], rtol=1e-10, atol=1e-12 * np.abs(red_s[:416]).max() * reps)
+    np.testing.assert_allclose(red[416], reps * red_s[416], rtol=1e-12)
