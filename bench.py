@@ -293,7 +293,7 @@ def run_b200(args):
             "kernel_ms": {"rollout_fwd_kernel": f_ms, "rollout_bwd_kernel": b_ms},
             "fwd_kernel": {"achieved": ach_fwd, "frac": (ach_fwd / fp64_peak) if ach_fwd else None},
             # hardware-side view (ncu, profiles/README.md): share of cycles the FP64 pipe is busy
-            "ncu_fp64_pipe_active_pct": {"rollout_fwd_kernel": 57.3, "rollout_bwd_kernel": 52.6, "source": "profiles/r1_ncu_bench_config.txt (not measured in this run)"},
+            "ncu_fp64_pipe_active_pct": {"rollout_fwd_kernel": 56.2, "rollout_bwd_kernel": 52.6, "source": "profiles/r1_ncu_bench_config.txt (not measured in this run)"},
             "flop_equiv_per_vehicle_step": {"fwd": FLOP_EQ_FWD, "fwd_adjoint": FLOP_EQ_FWD_ADJ},
             "whole_step_frac": FLOP_EQ_FWD_ADJ * value / world / 1e12 / fp64_peak,
         }
