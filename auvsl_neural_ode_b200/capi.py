@@ -23,7 +23,11 @@ EXPORTS = [
     "avs_set_terrain_grid", "avs_set_checkpoint_budget", "avs_whole_body_com", "avs_init_state_com", "avs_settle", "avs_ode",
     "avs_rollout", "avs_rollout_dev", "avs_rollout_grad", "avs_rollout_grad_dev", "avs_rmsprop_step_dev", "avs_rmsprop_step", "avs_reset_optimizer",
     "avs_stream", "avs_set_stream", "avs_use_own_stream", "avs_sync", "avs_kernel_launches", "avs_last_kernel_ms", "avs_measure_fp64_peak",
+    "avs_rollout_margins", "avs_comm_unique_id", "avs_comm_init_rank", "avs_comm_init_all", "avs_comm_destroy", "avs_comm_info",
+    "avs_allreduce_dev", "avs_allreduce", "avs_alloc_pinned", "avs_free_pinned", "avs_set_reduced",
 ]
+NUM_MARGINS = 6
+MARGIN_KINDS = ("contact |sinkage|", "Fx sign |wR - vx|", "slip clamps", "|pgc - pg| / pg", "|R - sinkage|", "arc |dtheta|")
 
 
 class AvsError(RuntimeError):
@@ -72,6 +76,17 @@ def lib():
         L.avs_kernel_launches.restype = C.c_longlong
         L.avs_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.avs_measure_fp64_peak.argtypes = [vp, C.POINTER(dbl)]
+        L.avs_rollout_margins.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp]
+        L.avs_comm_unique_id.argtypes = [vp]
+        L.avs_comm_init_rank.argtypes = [vp, vp, i32, i32]
+        L.avs_comm_init_all.argtypes = [C.POINTER(vp), i32]
+        L.avs_comm_destroy.argtypes = [vp]
+        L.avs_comm_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+        L.avs_allreduce_dev.argtypes = [vp, vp]
+        L.avs_allreduce.argtypes = [vp, vp]
+        L.avs_alloc_pinned.argtypes = [C.POINTER(vp), C.c_ulonglong]
+        L.avs_free_pinned.argtypes = [vp]
+        L.avs_set_reduced.argtypes = [vp, vp]
         _lib = L
     return _lib
 
@@ -107,6 +122,15 @@ def init_state_com(start21):
     out = np.zeros(21)
     lib().avs_init_state_com(_p(s), _p(out))
     return out
+
+
+def comm_unique_id():
+    """128-byte NCCL unique id (rank 0 creates it and ships it to the other ranks by any transport)."""
+    buf = C.create_string_buffer(128)
+    rc = lib().avs_comm_unique_id(buf)
+    if rc != 0:
+        raise AvsError(f"avs_comm_unique_id: {lib().avs_strerror(rc).decode()} (libnccl.so.2 not loadable?)")
+    return buf.raw
 
 
 def initialize_state(yaw, x, y, z, wz, vx, vy):
@@ -201,6 +225,15 @@ class Context:
         self._ck(lib().avs_rollout(self._h, N, T, substeps, _p(x0), _p(ctrl), _p(xl), _p(xf)))
         return xl, xf
 
+    def rollout_margins(self, x0, ctrl, T, substeps=10, want_list=True):
+        """Bekker only: rollout + branch margins [6][N] (kinds: MARGIN_KINDS; see include/avsim.h)."""
+        x0, ctrl = _f64(x0), _f64(ctrl)
+        N = x0.shape[1]
+        xl = np.zeros((T, 23, N)) if want_list else None
+        xf, mg = np.zeros((21, N)), np.zeros((NUM_MARGINS, N))
+        self._ck(lib().avs_rollout_margins(self._h, N, T, substeps, _p(x0), _p(ctrl), _p(xl), _p(xf), _p(mg)))
+        return xl, xf, mg
+
     def rollout_grad(self, x0, ctrl, gt, T, substeps=10, explode_thresh=100.0, explode_mode=0, per_sample=True):
         x0, ctrl, gt = _f64(x0), _f64(ctrl), _f64(gt)
         N = x0.shape[1]
@@ -219,13 +252,35 @@ class Context:
         self._ck(lib().avs_rollout_grad_dev(self._h, N, T, substeps, d_x0, d_ctrl, d_gt, float(explode_thresh), int(explode_mode),
                                             d_loss or None, d_reduced or None, d_grad_live or None))
 
-    def rmsprop_step_dev(self, d_reduced, lr=1e-3, l1_weight=0.0):
-        self._ck(lib().avs_rmsprop_step_dev(self._h, d_reduced, float(lr), float(l1_weight)))
+    def rmsprop_step_dev(self, d_reduced=0, lr=1e-3, l1_weight=0.0):
+        self._ck(lib().avs_rmsprop_step_dev(self._h, d_reduced or None, float(lr), float(l1_weight)))
 
     def rmsprop_step(self, reduced_host, lr=1e-3, l1_weight=0.0):
         r = _f64(reduced_host)
         assert r.size == REDUCED_LEN
         self._ck(lib().avs_rmsprop_step(self._h, _p(r), float(lr), float(l1_weight)))
+
+    # ---- multi-GPU (one NCCL rank per context; include/avsim.h "multi-GPU")
+    def comm_init_rank(self, uid_bytes, world, rank):
+        buf = C.create_string_buffer(bytes(uid_bytes), 128)
+        self._ck(lib().avs_comm_init_rank(self._h, buf, int(world), int(rank)))
+
+    def comm_destroy(self):
+        self._ck(lib().avs_comm_destroy(self._h))
+
+    def comm_info(self):
+        w, r, v = C.c_int(), C.c_int(), C.c_int()
+        self._ck(lib().avs_comm_info(self._h, C.byref(w), C.byref(r), C.byref(v)))
+        return w.value, r.value, v.value
+
+    def allreduce_dev(self, d_reduced=0):
+        """In-place ncclAllReduce(sum) of 418 doubles on the context's stream (0 = the context's own reduced buffer)."""
+        self._ck(lib().avs_allreduce_dev(self._h, d_reduced or None))
+
+    def allreduce(self, want_host=True):
+        out = np.zeros(REDUCED_LEN) if want_host else None
+        self._ck(lib().avs_allreduce(self._h, _p(out)))
+        return out
 
     def reset_optimizer(self):
         self._ck(lib().avs_reset_optimizer(self._h))

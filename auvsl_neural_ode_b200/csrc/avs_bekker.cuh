@@ -299,7 +299,15 @@ AVS_HD void bekker_nodes_vec(const BekNodeParams& k, const double* th, const dou
 // How the 12 nodes of an arc are evaluated: inline, four at a time (host harness, single-ODE kernels).  The rollout kernel
 // substitutes a policy that runs the same routine as ONE non-inlined function called three times per arc, so that the hot
 // quadrature code is ~350 instructions that stay in the instruction cache instead of six unrolled copies (avs_dev.cuh).
+// Branch-margin probe (same kinds and definitions as oracle/jackal_oracle.hpp): how far each value-dependent
+// predicate of the Bekker path was from flipping.  The node-evaluation policy doubles as the probe sink; the production
+// policies ignore it (the calls compile away), the diagnostic instantiation keeps per-lane minima.
+//   0 |sinkage| (contact on/off)   1 |w R - vx| (sign of Fx)   2 slip clamps at 1e-3   3 |pgc - pg| / pg
+//   4 |R - sinkage| (zr clamp)     5 |dtheta| of the non-empty arcs (trapezoid loop bound)
+constexpr int kNumMargins = 6;
+
 struct BekNodesInline {
+    AVS_HD void margin(int, double) const {}
     AVS_HD void operator()(const BekNodeParams& q, const double* th, const double* s, const double* c, double* fx, double* fy, double* fz) const {
         bekker_nodes_vec<4>(q, th, s, c, fx, fy, fz);
         bekker_nodes_vec<4>(q, th + 4, s + 4, c + 4, fx + 4, fy + 4, fz + 4);
@@ -373,11 +381,16 @@ AVS_HD void bekker_tire_fwd(const ModelConst& mc, double cvx, double cvy, double
     const double slip_ratio = 1 - (vx_c / wr_c);
     const double slip_angle = tanh_f64(cvy / fabs(vx_c));
 
+    eval.margin(0, fabs(sinkage));
+    eval.margin(1, fabs(vel_x_tan - cvx));
+    eval.margin(2, fabs(fabs(cvx) - 1e-3));
+    eval.margin(2, fabs(fabs(vel_x_tan) - 1e-3));
     double Fx = 0.0, Fy = 0.0, Fz = 0.0;
     if (sinkage > 0.0) {  // BekkerDynamics.cpp:81
         BekkerCtx k;
         k.R = 0.098; k.b = 0.05; k.K = .0254; k.c = 8.62; k.pg = 100;  // BekkerTireModel.cpp:5-14, .h:34-35
         const double k0 = 2195, Au = 192400;
+        eval.margin(4, fabs(k.R - sinkage));
         const double zr = sinkage > k.R ? k.R : sinkage;  // :219
         k.slip_ratio = slip_ratio;
         k.tan_sa = tan(slip_angle);
@@ -385,6 +398,7 @@ AVS_HD void bekker_tire_fwd(const ModelConst& mc, double cvx, double cvy, double
         k.n = n0 + (n1 * fabs(slip_ratio));
         k.kk = (kc / k.b) + kphi;
         const double pgc = k.kk * pow_pos(zr, k.n);
+        eval.margin(3, fabs(pgc - k.pg) / k.pg);
         if (pgc < k.pg) k.ze = zr;
         else k.ze = pow_pos(k.pg / k.kk, 1.0 / k.n);
         k.ku = k0 + (Au * k.ze);
@@ -399,6 +413,12 @@ AVS_HD void bekker_tire_fwd(const ModelConst& mc, double cvx, double cvy, double
         k.cos_tr = 1 - ur;
         k.cos_tc = 1 - uc; k.sin_tc = sqrt(uc * (2 - uc));
         const double sin_tr = -sqrt(ur * (2 - ur));
+        {   // arc widths as BekkerTireModel::integrate forms them (:165): front, centre, rear
+            const double df = (k.theta_f - k.theta_c) / 10.0, dc = (k.theta_c - (-k.theta_c)) / 10.0, dr = ((-k.theta_c) - k.theta_r) / 10.0;
+            if (df != 0.0) eval.margin(5, fabs(df));
+            if (dc != 0.0) eval.margin(5, fabs(dc));
+            if (dr != 0.0) eval.margin(5, fabs(dr));
+        }
         const double bt_R = k.R * k.b;
         const Bek3 If = bekker_integrate_vec<0>(k, k.theta_f, k.theta_c, k.sin_tc, k.cos_tc, k.sin_tf, k.cos_tf, eval);
         const Bek3 Ir = bekker_integrate_vec<2>(k, -k.theta_c, k.theta_r, sin_tr, k.cos_tr, -k.sin_tc, k.cos_tc, eval);

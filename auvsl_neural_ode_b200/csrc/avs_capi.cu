@@ -1,10 +1,15 @@
 // avs_capi.cu — the C ABI declared in include/avsim.h: context, device memory, launches.
 // No torch, no CPU fallback: every compute entry point ends in a kernel launch on the context's stream.
+#include <dlfcn.h>
+
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
+
+#include <nccl.h>  // types and enums only: the library is bound at run time (dlopen), libavsim.so does not link it
 
 #include "../../include/avsim.h"
 #include "avs_kernels.h"
@@ -45,6 +50,9 @@ struct avs_ctx {
     DevBuf grid_h, grid_s, ztab;
     DevBuf ckpt, act, gps, loss, reduced, flags, settle;
     DevBuf in_x0, in_ctrl, in_gt, out_list, out_final, io_a, io_b, io_c;
+    DevBuf margins;
+    ncclComm_t comm = nullptr;  // one communicator rank per context (avs_comm_*)
+    int world = 1, rank = 0;
     long long launches = 0;
     int plan_N = -1;
     size_t plan_per_vehicle = 0, plan_chunk = 0;
@@ -67,6 +75,90 @@ static int fail(avs_ctx* c, int code, const char* fmt, ...) {
     do {                                                                                                      \
         cudaError_t e__ = (call);                                                                             \
         if (e__ != cudaSuccess) return fail(ctx, AVS_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+// ---- one __constant__ model per translation unit, shared by every context of a device -------------------------------
+// upload_model (avs_dev.cuh) and the launch that reads it are ordered within ONE stream only.  Two contexts on the same
+// GPU use different streams, so a later context's upload could overtake an earlier context's still-running kernel.  Every
+// launch therefore waits for the previous launch on that device when it came from a different stream (a no-op for the
+// usual one-context-per-GPU set-up) and leaves an event behind.
+namespace {
+struct DeviceOrder {
+    std::mutex mu;
+    cudaEvent_t ev = nullptr;
+    cudaStream_t last = nullptr;
+    bool any = false;
+};
+DeviceOrder g_order[64];
+}  // namespace
+static cudaError_t pre_launch(avs_ctx* c) {
+    DeviceOrder& o = g_order[c->device & 63];
+    std::lock_guard<std::mutex> lk(o.mu);
+    if (o.any && o.last != c->stream) return cudaStreamWaitEvent(c->stream, o.ev, 0);
+    return cudaSuccess;
+}
+static cudaError_t post_launch(avs_ctx* c) {
+    DeviceOrder& o = g_order[c->device & 63];
+    std::lock_guard<std::mutex> lk(o.mu);
+    if (!o.ev) {
+        cudaError_t e = cudaEventCreateWithFlags(&o.ev, cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+    }
+    o.last = c->stream;
+    o.any = true;
+    return cudaEventRecord(o.ev, c->stream);
+}
+#define LAUNCH(call)            \
+    do {                        \
+        CK(pre_launch(ctx));    \
+        CK(call);               \
+        CK(post_launch(ctx));   \
+    } while (0)
+
+// ---- NCCL, bound at run time --------------------------------------------------------------------------------------
+// dlopen("libnccl.so.2") returns the copy the process already maps (a Python process that imported torch: torch's bundled
+// NCCL; a plain C++ host: the system library), so libavsim.so never mixes two NCCL builds in one process.
+namespace {
+struct NcclApi {
+    void* h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    ncclResult_t (*GetVersion)(int*) = nullptr;
+    std::string err;
+};
+NcclApi* nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            api.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (api.h) break;
+        }
+        if (!api.h) { api.err = std::string("dlopen(libnccl.so.2): ") + dlerror(); return; }
+#define AVS_BIND(field, sym)                                                                 \
+    api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.h, sym));                    \
+    if (!api.field && api.err.empty()) api.err = std::string("libnccl: missing symbol ") + sym;
+        AVS_BIND(GetUniqueId, "ncclGetUniqueId")
+        AVS_BIND(CommInitRank, "ncclCommInitRank")
+        AVS_BIND(CommInitAll, "ncclCommInitAll")
+        AVS_BIND(CommDestroy, "ncclCommDestroy")
+        AVS_BIND(AllReduce, "ncclAllReduce")
+        AVS_BIND(GetErrorString, "ncclGetErrorString")
+        AVS_BIND(GetVersion, "ncclGetVersion")
+#undef AVS_BIND
+    });
+    return &api;
+}
+}  // namespace
+#define CKN(call)                                                                                                       \
+    do {                                                                                                                \
+        ncclResult_t r__ = (call);                                                                                      \
+        if (r__ != ncclSuccess) return fail(ctx, AVS_E_COMM, "%s: %s (%s:%d)", #call, nccl_api()->GetErrorString(r__), __FILE__, __LINE__); \
     } while (0)
 
 static void load_weights(avs_ctx* c) {
@@ -99,6 +191,7 @@ const char* avs_strerror(int code) {
         case AVS_E_CUDA: return "CUDA error or no usable device";
         case AVS_E_STATE: return "call not valid in this configuration";
         case AVS_E_NOMEM: return "out of memory";
+        case AVS_E_COMM: return "NCCL error or communicator not initialised";
     }
     return "unknown";
 }
@@ -154,6 +247,7 @@ int avs_create(avs_ctx** out, int device, int tire_model) {
         ctx->mc.ztab = ctx->ztab.as<double>();
     }
     if (!ok) { avs_destroy(ctx); return AVS_E_CUDA; }
+    if (cudaMemcpy(ctx->d_params, ctx->params, sizeof(ctx->params), cudaMemcpyHostToDevice) != cudaSuccess) { avs_destroy(ctx); return AVS_E_CUDA; }
     *out = ctx;
     return avs_reset_optimizer(ctx);
 }
@@ -162,6 +256,8 @@ void avs_destroy(avs_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm && nccl_api()->CommDestroy) nccl_api()->CommDestroy(ctx->comm);
+    ctx->margins.release();
     DevBuf* bufs[] = {&ctx->grid_h, &ctx->grid_s, &ctx->ztab, &ctx->ckpt, &ctx->act, &ctx->gps, &ctx->loss, &ctx->reduced, &ctx->flags, &ctx->settle,
                       &ctx->in_x0, &ctx->in_ctrl, &ctx->in_gt, &ctx->out_list, &ctx->out_final, &ctx->io_a, &ctx->io_b, &ctx->io_c};
     for (DevBuf* b : bufs) b->release();
@@ -265,7 +361,7 @@ int avs_settle(avs_ctx* ctx, double* state21_out) {
     if (!ctx || !state21_out) return fail(ctx, AVS_E_ARG, "avs_settle: null argument");
     CK(cudaSetDevice(ctx->device));
     CK(ctx->settle.reserve(21 * sizeof(double)));
-    CK(launch_settle(ctx->tire, ctx->mc, live(ctx), ctx->settle.as<double>(), ctx->stream));
+    LAUNCH(launch_settle(ctx->tire, ctx->mc, live(ctx), ctx->settle.as<double>(), ctx->stream));
     ctx->launches++;
     CK(cudaMemcpyAsync(state21_out, ctx->settle.p, 21 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -279,30 +375,46 @@ int avs_ode(avs_ctx* ctx, int N, const double* x, const double* u, double* xd) {
     CK(ctx->io_a.reserve(21 * n * 8)); CK(ctx->io_b.reserve(2 * n * 8)); CK(ctx->io_c.reserve(21 * n * 8));
     CK(cudaMemcpyAsync(ctx->io_a.p, x, 21 * n * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->io_b.p, u, 2 * n * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CK(launch_ode(ctx->tire, ctx->mc, live(ctx), N, ctx->io_a.as<double>(), ctx->io_b.as<double>(), ctx->io_c.as<double>(), ctx->stream));
+    LAUNCH(launch_ode(ctx->tire, ctx->mc, live(ctx), N, ctx->io_a.as<double>(), ctx->io_b.as<double>(), ctx->io_c.as<double>(), ctx->stream));
     ctx->launches++;
     CK(cudaMemcpyAsync(xd, ctx->io_c.p, 21 * n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return AVS_OK;
 }
 
-int avs_rollout_dev(avs_ctx* ctx, int N, int T, int substeps, const double* d_x0, const double* d_ctrl, double* d_x_list, double* d_x_final) {
+static int rollout_dev_impl(avs_ctx* ctx, int N, int T, int substeps, const double* d_x0, const double* d_ctrl, double* d_x_list, double* d_x_final,
+                            double* d_margins) {
     if (!ctx || N <= 0 || T < 1 || substeps < 1 || !d_x0 || (T > 1 && !d_ctrl)) return fail(ctx, AVS_E_ARG, "avs_rollout: bad argument (N=%d T=%d substeps=%d)", N, T, substeps);
+    if (d_margins && ctx->tire != AVS_TIRE_BEKKER) return fail(ctx, AVS_E_STATE, "avs_rollout_margins: branch margins exist for the Bekker tire model only");
     CK(cudaSetDevice(ctx->device));
     RolloutArgs a;
     memset(&a, 0, sizeof(a));
-    a.N = N; a.Nc = N; a.T = T; a.substeps = substeps; a.x0 = d_x0; a.ctrl = d_ctrl; a.x_list = d_x_list; a.x_final = d_x_final;
+    a.N = N; a.Nc = N; a.T = T; a.substeps = substeps; a.x0 = d_x0; a.ctrl = d_ctrl; a.x_list = d_x_list; a.x_final = d_x_final; a.margin = d_margins;
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-    CK(launch_rollout_fwd(ctx->tire, ctx->terr, false, ctx->mc, live(ctx), a, ctx->stream));
+    LAUNCH(launch_rollout_fwd(ctx->tire, ctx->terr, false, ctx->mc, live(ctx), a, ctx->stream));
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     ctx->ev_fwd = true; ctx->ev_bwd = false;
     ctx->launches++;
     return AVS_OK;
 }
 
+int avs_rollout_dev(avs_ctx* ctx, int N, int T, int substeps, const double* d_x0, const double* d_ctrl, double* d_x_list, double* d_x_final) {
+    return rollout_dev_impl(ctx, N, T, substeps, d_x0, d_ctrl, d_x_list, d_x_final, nullptr);
+}
+
+static int rollout_host_impl(avs_ctx* ctx, int N, int T, int substeps, const double* x0, const double* ctrl, double* x_list, double* x_final, double* margins);
 int avs_rollout(avs_ctx* ctx, int N, int T, int substeps, const double* x0, const double* ctrl, double* x_list, double* x_final) {
+    return rollout_host_impl(ctx, N, T, substeps, x0, ctrl, x_list, x_final, nullptr);
+}
+int avs_rollout_margins(avs_ctx* ctx, int N, int T, int substeps, const double* x0, const double* ctrl, double* x_list, double* x_final, double* margins) {
+    if (!margins) return fail(ctx, AVS_E_ARG, "avs_rollout_margins: margins is null");
+    return rollout_host_impl(ctx, N, T, substeps, x0, ctrl, x_list, x_final, margins);
+}
+
+static int rollout_host_impl(avs_ctx* ctx, int N, int T, int substeps, const double* x0, const double* ctrl, double* x_list, double* x_final, double* margins) {
     if (!ctx || N <= 0 || T < 1 || substeps < 1 || !x0 || (T > 1 && !ctrl)) return fail(ctx, AVS_E_ARG, "avs_rollout: bad argument (N=%d T=%d substeps=%d)", N, T, substeps);
     CK(cudaSetDevice(ctx->device));
+    if (margins) CK(ctx->margins.reserve((size_t)kNumMargins * N * 8));
     const size_t n = (size_t)N;
     const size_t b_x0 = 21 * n * 8, b_ctrl = (size_t)(T - 1) * 2 * n * 8, b_list = (size_t)T * 23 * n * 8;
     CK(ctx->in_x0.reserve(b_x0));
@@ -311,9 +423,10 @@ int avs_rollout(avs_ctx* ctx, int N, int T, int substeps, const double* x0, cons
     if (x_final) CK(ctx->out_final.reserve(b_x0));
     CK(cudaMemcpyAsync(ctx->in_x0.p, x0, b_x0, cudaMemcpyHostToDevice, ctx->stream));
     if (b_ctrl) CK(cudaMemcpyAsync(ctx->in_ctrl.p, ctrl, b_ctrl, cudaMemcpyHostToDevice, ctx->stream));
-    int rc = avs_rollout_dev(ctx, N, T, substeps, ctx->in_x0.as<double>(), ctx->in_ctrl.as<double>(), x_list ? ctx->out_list.as<double>() : nullptr,
-                             x_final ? ctx->out_final.as<double>() : nullptr);
+    int rc = rollout_dev_impl(ctx, N, T, substeps, ctx->in_x0.as<double>(), ctx->in_ctrl.as<double>(), x_list ? ctx->out_list.as<double>() : nullptr,
+                              x_final ? ctx->out_final.as<double>() : nullptr, margins ? ctx->margins.as<double>() : nullptr);
     if (rc) return rc;
+    if (margins) CK(cudaMemcpyAsync(margins, ctx->margins.p, (size_t)kNumMargins * N * 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (x_list) CK(cudaMemcpyAsync(x_list, ctx->out_list.p, b_list, cudaMemcpyDeviceToHost, ctx->stream));
     if (x_final) CK(cudaMemcpyAsync(x_final, ctx->out_final.p, b_x0, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -361,21 +474,21 @@ static int rollout_grad_impl(avs_ctx* ctx, int N, int T, int substeps, const dou
         a.N = N; a.Nc = (int)cnt; a.T = T; a.substeps = substeps;
         a.x0 = d_x0 + begin; a.ctrl = d_ctrl + begin; a.gt = d_gt + begin; a.ckpt = ctx->ckpt.as<double>(); a.act = ctx->act.as<double>();
         a.loss = d_loss + begin; a.gps = d_grad_live + begin;
-        CK(launch_rollout_fwd(AVS_TIRE_NN, ctx->terr, true, ctx->mc, live(ctx), a, ctx->stream));
+        LAUNCH(launch_rollout_fwd(AVS_TIRE_NN, ctx->terr, true, ctx->mc, live(ctx), a, ctx->stream));
         if (begin == 0 && cnt == n) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
         if (begin == 0 && host_gt) {
             CK(cudaMemcpyAsync(const_cast<double*>(d_gt), host_gt, (size_t)T * 3 * n * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
             CK(cudaEventRecord(ctx->ev_copy, ctx->copy_stream));
             CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy, 0));
         }
-        CK(launch_rollout_bwd(ctx->terr, ctx->mc, live(ctx), a, ctx->stream));
+        LAUNCH(launch_rollout_bwd(ctx->terr, ctx->mc, live(ctx), a, ctx->stream));
         ctx->launches += 2;
     }
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     ctx->ev_fwd = (chunk == n); ctx->ev_bwd = (chunk == n);
     if (d_reduced) {
         if (explode_mode == 1) CK(ctx->flags.reserve(n));
-        CK(launch_filter_reduce(d_grad_live, d_loss, N, explode_thresh, explode_mode, ctx->flags.as<unsigned char>(), d_reduced, ctx->stream));
+        LAUNCH(launch_filter_reduce(d_grad_live, d_loss, N, explode_thresh, explode_mode, ctx->flags.as<unsigned char>(), d_reduced, ctx->stream));
         ctx->launches += (explode_mode == 1) ? 2 : 1;
     }
     return AVS_OK;
@@ -415,26 +528,138 @@ int avs_reset_optimizer(avs_ctx* ctx) {
     CK(cudaSetDevice(ctx->device));
     std::vector<double> ones(AVS_NUM_NN_PARAMS, 1.0);  // m_squared_grad = Ones (Trainer.cpp:63)
     CK(cudaMemcpyAsync(ctx->d_sq, ones.data(), sizeof(double) * AVS_NUM_NN_PARAMS, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_params, ctx->params, sizeof(ctx->params), cudaMemcpyHostToDevice, ctx->stream));
+    // only the squared-gradient state is reset; after a device RMSProp step d_params is the authoritative copy and the
+    // host snapshot is stale, so it must not be uploaded here (avs_create uploads the initial parameters itself)
     CK(cudaStreamSynchronize(ctx->stream));
     return AVS_OK;
 }
 
 int avs_rmsprop_step_dev(avs_ctx* ctx, const double* d_reduced, double lr, double l1_weight) {
-    if (!ctx || !d_reduced) return fail(ctx, AVS_E_ARG, "avs_rmsprop_step_dev: null argument");
+    if (!ctx) return AVS_E_ARG;
+    if (!d_reduced) {  // the context's own buffer: what the host-buffer avs_rollout_grad (+ avs_allreduce) left on the device
+        if (!ctx->reduced.p) return fail(ctx, AVS_E_STATE, "avs_rmsprop_step_dev: no reduced gradient on the device yet");
+        d_reduced = ctx->reduced.as<double>();
+    }
     CK(cudaSetDevice(ctx->device));
-    CK(launch_rmsprop(ctx->d_params, ctx->d_sq, d_reduced, lr, l1_weight, ctx->stream));
+    LAUNCH(launch_rmsprop(ctx->d_params, ctx->d_sq, d_reduced, lr, l1_weight, ctx->stream));
     ctx->launches++;
     ctx->params_dirty_on_device = true;
     return AVS_OK;
 }
 
-int avs_rmsprop_step(avs_ctx* ctx, const double* reduced_host, double lr, double l1_weight) {
-    if (!ctx || !reduced_host) return fail(ctx, AVS_E_ARG, "avs_rmsprop_step: null argument");
+int avs_set_reduced(avs_ctx* ctx, const double* reduced_host) {
+    if (!ctx || !reduced_host) return fail(ctx, AVS_E_ARG, "avs_set_reduced: null argument");
     CK(cudaSetDevice(ctx->device));
     CK(ctx->reduced.reserve(AVS_REDUCED_LEN * 8));
     CK(cudaMemcpyAsync(ctx->reduced.p, reduced_host, AVS_REDUCED_LEN * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));  // the caller's buffer may be pageable and short-lived
+    return AVS_OK;
+}
+
+int avs_rmsprop_step(avs_ctx* ctx, const double* reduced_host, double lr, double l1_weight) {
+    if (!ctx || !reduced_host) return fail(ctx, AVS_E_ARG, "avs_rmsprop_step: null argument");
+    int rc = avs_set_reduced(ctx, reduced_host);
+    if (rc) return rc;
     return avs_rmsprop_step_dev(ctx, ctx->reduced.as<double>(), lr, l1_weight);
+}
+
+// ---- pinned host staging ----------------------------------------------------------------------------------------------
+int avs_alloc_pinned(void** out, unsigned long long bytes) {
+    if (!out || bytes == 0) return AVS_E_ARG;
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, (size_t)bytes, cudaHostAllocDefault);
+    if (e == cudaErrorMemoryAllocation) return AVS_E_NOMEM;
+    return e == cudaSuccess ? AVS_OK : AVS_E_CUDA;
+}
+int avs_free_pinned(void* p) {
+    if (!p) return AVS_OK;
+    return cudaFreeHost(p) == cudaSuccess ? AVS_OK : AVS_E_CUDA;
+}
+
+// ---- multi-GPU: one communicator rank per context, one all-reduce of reduced[418] per training step ---------------------
+int avs_comm_unique_id(char* id128) {
+    if (!id128) return AVS_E_ARG;
+    NcclApi* api = nccl_api();
+    if (!api->err.empty()) return AVS_E_COMM;
+    static_assert(sizeof(ncclUniqueId) == AVS_COMM_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId id;
+    if (api->GetUniqueId(&id) != ncclSuccess) return AVS_E_COMM;
+    memcpy(id128, &id, sizeof(id));
+    return AVS_OK;
+}
+int avs_comm_init_rank(avs_ctx* ctx, const char* id128, int world, int rank) {
+    if (!ctx || !id128 || world < 1 || rank < 0 || rank >= world) return fail(ctx, AVS_E_ARG, "avs_comm_init_rank: bad argument (world=%d rank=%d)", world, rank);
+    NcclApi* api = nccl_api();
+    if (!api->err.empty()) return fail(ctx, AVS_E_COMM, "%s", api->err.c_str());
+    if (ctx->comm) return fail(ctx, AVS_E_STATE, "avs_comm_init_rank: the context already has a communicator");
+    CK(cudaSetDevice(ctx->device));
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    CKN(api->CommInitRank(&ctx->comm, world, id, rank));
+    ctx->world = world; ctx->rank = rank;
+    return AVS_OK;
+}
+int avs_comm_init_all(avs_ctx** ctxs, int n) {
+    if (!ctxs || n < 1 || n > 64) return AVS_E_ARG;
+    avs_ctx* ctx = ctxs[0];
+    NcclApi* api = nccl_api();
+    if (!api->err.empty()) return fail(ctx, AVS_E_COMM, "%s", api->err.c_str());
+    int devs[64];
+    ncclComm_t comms[64];
+    for (int i = 0; i < n; i++) {
+        if (!ctxs[i] || ctxs[i]->comm) return fail(ctx, AVS_E_STATE, "avs_comm_init_all: context %d is null or already has a communicator", i);
+        devs[i] = ctxs[i]->device;
+        for (int j = 0; j < i; j++) if (devs[j] == devs[i]) return fail(ctx, AVS_E_ARG, "avs_comm_init_all: contexts %d and %d share device %d", j, i, devs[i]);
+    }
+    CKN(api->CommInitAll(comms, n, devs));
+    for (int i = 0; i < n; i++) { ctxs[i]->comm = comms[i]; ctxs[i]->world = n; ctxs[i]->rank = i; }
+    return AVS_OK;
+}
+int avs_comm_destroy(avs_ctx* ctx) {
+    if (!ctx) return AVS_E_ARG;
+    if (ctx->comm) {
+        CK(cudaSetDevice(ctx->device));
+        CK(cudaStreamSynchronize(ctx->stream));
+        CKN(nccl_api()->CommDestroy(ctx->comm));
+        ctx->comm = nullptr; ctx->world = 1; ctx->rank = 0;
+    }
+    return AVS_OK;
+}
+int avs_comm_info(const avs_ctx* ctx, int* world, int* rank, int* nccl_version) {
+    if (!ctx) return AVS_E_ARG;
+    if (world) *world = ctx->world;
+    if (rank) *rank = ctx->rank;
+    if (nccl_version) {
+        *nccl_version = 0;
+        NcclApi* api = nccl_api();
+        if (api->err.empty()) api->GetVersion(nccl_version);
+    }
+    return AVS_OK;
+}
+int avs_allreduce_dev(avs_ctx* ctx, double* d_reduced) {
+    if (!ctx) return AVS_E_ARG;
+    if (!d_reduced) {
+        if (!ctx->reduced.p) return fail(ctx, AVS_E_STATE, "avs_allreduce_dev: no reduced gradient on the device yet");
+        d_reduced = ctx->reduced.as<double>();
+    }
+    if (!ctx->comm) {
+        if (ctx->world == 1) return AVS_OK;  // single rank: the local sum is the global sum
+        return fail(ctx, AVS_E_COMM, "avs_allreduce_dev: no communicator");
+    }
+    CK(cudaSetDevice(ctx->device));
+    // in place, on the context's stream: ordered after the filter/reduce kernel that produced it and before the RMSProp
+    // kernel that consumes it; no host hop
+    CKN(nccl_api()->AllReduce(d_reduced, d_reduced, AVS_REDUCED_LEN, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+    return AVS_OK;
+}
+int avs_allreduce(avs_ctx* ctx, double* reduced_host_out) {
+    int rc = avs_allreduce_dev(ctx, nullptr);
+    if (rc) return rc;
+    if (reduced_host_out) {
+        CK(cudaMemcpyAsync(reduced_host_out, ctx->reduced.p, AVS_REDUCED_LEN * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return AVS_OK;
 }
 
 void* avs_stream(avs_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }

@@ -38,8 +38,16 @@ template <int BLOCK> __device__ __noinline__ void bekker_nodes4_call(int slot) {
 #pragma unroll
     for (int i = 0; i < 4; i++) { S[25 + i] = fx[i]; S[29 + i] = fy[i]; S[33 + i] = fz[i]; }
 }
-template <int BLOCK> struct BekNodesCall {
+// MARGIN: the diagnostic rollout keeps the per-lane minima of the kNumMargins branch margins in the scratch columns that
+// follow the node hand-off columns
+template <int BLOCK, bool MARGIN = false> struct BekNodesCall {
     int slot;
+    __device__ __forceinline__ void margin(int kind, double v) const {
+        if (MARGIN) {
+            const Scratch<BLOCK> M = scratch_col<BLOCK>(slot + kBekScratch);
+            M[kind] = fmin(M[kind], v);
+        }
+    }
     __device__ __forceinline__ void operator()(const BekNodeParams& q, const double* th, const double* s, const double* c, double* fx, double* fy, double* fz) const {
         const Scratch<BLOCK> S = scratch_col<BLOCK>(slot);
         S[0] = q.R; S[1] = q.n; S[2] = q.cos_end; S[3] = q.coef; S[4] = q.A; S[5] = q.om; S[6] = q.sin_tf; S[7] = q.B; S[8] = q.RomT; S[9] = q.C;
@@ -56,24 +64,24 @@ template <int BLOCK> struct BekNodesCall {
 };
 
 // K = f(T):  T, K = scratch slots (13 columns each); act (STORE_ACT) = this lane's activation record of the stage
-template <int TIRE, int TERR, int BLOCK, bool STORE_ACT>
+template <int TIRE, int TERR, int BLOCK, bool STORE_ACT, bool MARGIN = false>
 __device__ __noinline__ void ode_fwd_call(int lane0, int slotT, int slotK, double ul, double ur, double* act) {
     const Scratch<BLOCK> T = scratch_col<BLOCK>(slotT), K = scratch_col<BLOCK>(slotK);
     double X[13], Xd[13];
 #pragma unroll
     for (int c = 0; c < 13; c++) X[c] = T[c];
-    if (TIRE == TIRE_BEKKER) ode_fwd<1, TIRE, TERR, STORE_ACT, BekNodesCall<BLOCK>>(c_mc, lane0, X, ul, ur, Xd, nullptr, ActOutPtr{act}, BekNodesCall<BLOCK>{kFwdScratch});
+    if (TIRE == TIRE_BEKKER) ode_fwd<1, TIRE, TERR, STORE_ACT, BekNodesCall<BLOCK, MARGIN>>(c_mc, lane0, X, ul, ur, Xd, nullptr, ActOutPtr{act}, BekNodesCall<BLOCK, MARGIN>{kFwdScratch});
     else ode_fwd<1, TIRE, TERR, STORE_ACT>(c_mc, lane0, X, ul, ur, Xd, nullptr, ActOutPtr{act});
 #pragma unroll
     for (int c = 0; c < 13; c++) K[c] = Xd[c];
 }
-template <int TIRE, int TERR, int BLOCK, bool STORE_ACT> struct OdeFwdCall {
+template <int TIRE, int TERR, int BLOCK, bool STORE_ACT, bool MARGIN = false> struct OdeFwdCall {
     int lane0, slotT, slotK;
     double ul, ur;
     double* act_step;         // this lane's record of stage 0 of the current RK4 step
     size_t act_stage_stride;  // doubles between consecutive stages
     __device__ __forceinline__ void operator()(Scratch<BLOCK>, Scratch<BLOCK>, int s) const {
-        ode_fwd_call<TIRE, TERR, BLOCK, STORE_ACT>(lane0, slotT, slotK, ul, ur, STORE_ACT ? act_step + (size_t)s * act_stage_stride : nullptr);
+        ode_fwd_call<TIRE, TERR, BLOCK, STORE_ACT, MARGIN>(lane0, slotT, slotK, ul, ur, STORE_ACT ? act_step + (size_t)s * act_stage_stride : nullptr);
     }
 };
 
@@ -130,29 +138,10 @@ template <int TERR, int BLOCK, bool STORE> struct FusedStep {
     }
 };
 
-// ---- producer / consumer hand-off of the weight-gradient operands ---------------------------------------
-// The reverse kernel is warp-specialised: warp 0 of a CTA (producer) runs the state adjoint, warp 1 (consumer)
-// owns the 104 gradient accumulators IN REGISTERS and does nothing but  g += outer products.  Per RK4 stage the
-// producer stages the 37 operands (kGradOps) of its lane in one of two shared-memory buffers and signals
-// "full"; the consumer reads them, signals "empty" and runs the 104 DFMA.  Named barriers 1,2 = full[0..1],
-// 3,4 = empty[0..1], 64 participants each.  (Measured: with the read-modify-write of 104 shared-memory
-// accumulators inside the producer the kernel took 21.3 ms, without it 12.8 ms.)
+// ---- named barriers of the warp-specialised reverse kernel (producer warp + consumer warp, 64 participants) -----------
 constexpr int kBarFull = 1, kBarEmpty = 3;
 __device__ __forceinline__ void bar_sync64(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void bar_arrive64(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
-
-template <int BLOCK> struct StagingAcc {
-    double* stage0;  // this lane's column of staging buffer 0; buffer p starts kGradOps * BLOCK doubles further
-    int count;       // stages recorded so far by this warp
-    __device__ __forceinline__ void record(const double* op) {
-        const int p = count & 1;
-        if (count >= 2) bar_sync64(kBarEmpty + p);  // the consumer has drained this buffer
-        double* dst = stage0 + (size_t)p * kGradOps * BLOCK;
-#pragma unroll
-        for (int i = 0; i < kGradOps; i++) dst[i * BLOCK] = op[i];
-        bar_arrive64(kBarFull + p);  // st.shared ; bar.arrive  <->  bar.sync ; ld.shared  (PTX ISA producer/consumer pattern)
-    }
-};
 
 // 14-double record staged in shared memory as seven 16-byte pairs: element c of this lane at
 // base[((c >> 1) * BLOCK) * 2 + (c & 1)]  (base already includes lane * 2)
@@ -180,43 +169,6 @@ template <int BLOCK> struct ActInSmem {
     }
     __device__ __forceinline__ ActInSmem wheel(int) const { return *this; }
 };
-template <int BLOCK> __device__ __forceinline__ void act_prefetch(int slotACT, const double* src) {
-#pragma unroll
-    for (int i = 0; i < kActLen / 2; i++) {
-        const unsigned saddr = (unsigned)__cvta_generic_to_shared(g_smem + (size_t)slotACT * BLOCK + ((size_t)i * BLOCK + threadIdx.x) * 2);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(src + (size_t)i * kActPairStride) : "memory");
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-}
-
-// adjoint of stage s: LAM += J^T KB through the stage normalisation, KB <- adjoint of the previous stage's k,
-// weight-gradient operands staged for the consumer warp
-template <int TERR, int BLOCK>
-__device__ __noinline__ void ode_bwd_call(int lane0, int slotXS, int slotLAM, int slotG, int slotACT, double ul, double ur, const double* act_next,
-                                          int stage_count, int s) {
-    // (slotXS is dynamic: the record buffers alternate)
-    const PairCol<BLOCK> XS = pair_col<BLOCK>(slotXS);
-    const Scratch<BLOCK> LAM = scratch_col<BLOCK>(slotLAM), YB = scratch_col<BLOCK>(slotLAM + 13), KB = scratch_col<BLOCK>(slotLAM + 26);
-    StagingAcc<BLOCK> acc{g_smem + slotG * BLOCK + threadIdx.x, stage_count};
-    double X[13], Xb[13];
-#pragma unroll
-    for (int c = 0; c < 13; c++) X[c] = XS[c];
-    // once this stage's activation record is in registers, refill the shared-memory slots with the previous stage's
-    // record (HBM -> smem, asynchronous; a whole stage of compute later the stream's next advance() waits for it)
-    auto refill = [slotACT, act_next]() { if (act_next) act_prefetch<BLOCK>(slotACT, act_next); };
-    ode_bwd_nn<1, TERR>(c_mc, lane0, X, ul, ur, KB, Xb, acc, ActInSmem<BLOCK>{g_smem + (size_t)slotACT * BLOCK + (size_t)threadIdx.x * 2}, refill);
-    rk4_bwd_stage_update(XS, Xb, s, LAM, YB, KB);
-}
-template <int TERR, int BLOCK> struct OdeBwdCall {
-    int lane0, slotXA, slotXB, slotLAM, slotG, slotACT;
-    double ul, ur;
-    int* stage_counter;  // stages handed to the consumer warp so far
-    __device__ __forceinline__ void operator()(PairCol<BLOCK> XS, Scratch<BLOCK>, Scratch<BLOCK>, Scratch<BLOCK>, int s, const double* act_next) const {
-        const bool isA = XS.base == pair_col<BLOCK>(slotXA).base;
-        ode_bwd_call<TERR, BLOCK>(lane0, isA ? slotXA : slotXB, slotLAM, slotG, slotACT, ul, ur, act_next, (*stage_counter)++, s);
-    }
-};
-
 // ---- reverse kernel, split tire adjoint (rollout_bwd2_kernel) ---------------------------------------------------------
 // Consumer -> producer: per lane and stage the xy-net Jacobian, the gated z derivative and the terrain gradient
 // (kJLen doubles as four 16-byte pairs: jxx jyx | jxy jyy | dzg - | dax day), formed one stage AHEAD of the producer.
@@ -320,48 +272,6 @@ template <int BLOCK> struct CkptStreamRec {
         asm volatile("cp.async.wait_all;" ::: "memory");
         parity ^= 1;
         rec -= rec_stride;
-        remaining--;
-        prefetch_prev();
-    }
-};
-
-// Reverse record stream with one-record-ahead prefetch: while the adjoint of stage s runs (~8 k cycles), the
-// record of the stage before it is copied HBM -> this lane's shared-memory column by cp.async (LDGSTS), so the
-// HBM latency of the checkpoint stream is off the critical path of the single resident warp.
-template <int BLOCK> struct CkptStreamAsync {
-    const double* rec;   // current record of this vehicle in HBM (14 contiguous doubles)
-    size_t rec_stride;   // doubles between consecutive records = Nc * kCkRows
-    long remaining;      // records before the current one
-    int slotA, slotB, parity;
-    const double* actp;  // this lane's activation record (HBM) of the current stage
-    size_t act_stride;   // doubles between the activation records of consecutive stages = 4 * Nc * kActLen
-    int slotACT;
-    // token handed to the adjoint call: HBM address of the activation record it should prefetch next
-    __device__ __forceinline__ const double* act() const { return remaining > 0 ? actp - act_stride : nullptr; }
-    __device__ __forceinline__ PairCol<BLOCK> cur() const { return pair_col<BLOCK>(parity ? slotB : slotA); }
-    __device__ __forceinline__ void prefetch_prev() {
-        if (remaining <= 0) return;
-        const double* src = rec - rec_stride;
-        const int slot = parity ? slotA : slotB;
-#pragma unroll
-        for (int i = 0; i < kCkRows / 2; i++) {
-            const unsigned saddr = (unsigned)__cvta_generic_to_shared(g_smem + (size_t)slot * BLOCK + ((size_t)i * BLOCK + threadIdx.x) * 2);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(src + 2 * i) : "memory");
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    }
-    __device__ __forceinline__ void init() {  // synchronous load of the final-state record, then start the pipeline
-        const PairCol<BLOCK> dst = cur();
-#pragma unroll
-        for (int c = 0; c < kCkRows; c++) dst[c] = __ldg(rec + c);
-        prefetch_prev();
-        if (remaining > 0) act_prefetch<BLOCK>(slotACT, actp - act_stride);  // first stage to be reversed
-    }
-    __device__ __forceinline__ void advance() {
-        asm volatile("cp.async.wait_all;" ::: "memory");
-        parity ^= 1;
-        rec -= rec_stride;
-        actp -= act_stride;
         remaining--;
         prefetch_prev();
     }

@@ -7,7 +7,8 @@ namespace avs {
 // __launch_bounds__(.., 3): the register cap of three resident CTAs (170) is what makes ptxas pick the wide schedule for the
 // non-inlined stage callee (168 registers, 1 % back-to-back dependent FP64); without it ptxas settles on 128 registers and a
 // more serial order (measured: forward+store 14.1 ms vs 11.5 ms at N = 4096 x T = 200); with 2 it is 12.1 ms.
-template <int TIRE, int TERR, bool STORE>
+// MARGIN (Bekker only): diagnostic instantiation that also reports the branch margins of every trajectory (avs_bekker.cuh)
+template <int TIRE, int TERR, bool STORE, bool MARGIN = false>
 __global__ void __launch_bounds__(kFwdBlock, (TIRE == TIRE_NN ? 3 : 0)) rollout_fwd_kernel(const __grid_constant__ RolloutArgs a) {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     int n = gid >> 2;
@@ -28,24 +29,38 @@ __global__ void __launch_bounds__(kFwdBlock, (TIRE == TIRE_NN ? 3 : 0)) rollout_
         rollout_fwd_body<STORE>(a, n, lane0, valid, S, mk_step);
     } else {
         const size_t stage_stride = (size_t)4 * a.Nc * kActLen;
+        const Scratch<kFwdBlock> M = scratch_col<kFwdBlock>(kFwdScratch + kBekScratch);
+        if (MARGIN) {
+#pragma unroll
+            for (int k = 0; k < kNumMargins; k++) M[k] = 1e300;
+        }
         auto mk_step = [&a, n, lane0, writer, S, stage_stride](double ul, double ur) {
-            typedef OdeFwdCall<TIRE, TERR, kFwdBlock, false> Ode;
+            typedef OdeFwdCall<TIRE, TERR, kFwdBlock, false, MARGIN> Ode;
             return GenericStep<false, Ode, Scratch<kFwdBlock>>{Ode{lane0, 26, 39, ul, ur, nullptr, stage_stride}, a, n, lane0, writer, S};
         };
         rollout_fwd_body<false>(a, n, lane0, valid, S, mk_step);
+        if (MARGIN) {  // minimum over the four wheel lanes of the vehicle
+#pragma unroll
+            for (int k = 0; k < kNumMargins; k++) {
+                double m = M[k];
+                m = fmin(m, __shfl_xor_sync(0xffffffffu, m, 1));
+                m = fmin(m, __shfl_xor_sync(0xffffffffu, m, 2));
+                if (writer && a.margin) a.margin[(size_t)k * a.N + n] = m;
+            }
+        }
     }
 }
 
-template <int TIRE, int TERR, bool STORE>
+template <int TIRE, int TERR, bool STORE, bool MARGIN = false>
 static cudaError_t launch_fwd_t(const ModelConst& mc, const double* d_live, const RolloutArgs& a, cudaStream_t s) {
     const long long threads = (long long)a.Nc * 4;
     const int grid = (int)((threads + kFwdBlock - 1) / kFwdBlock);
-    const size_t smem = (size_t)(kFwdScratch + (TIRE == TIRE_BEKKER ? kBekScratch : 0)) * kFwdBlock * sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(rollout_fwd_kernel<TIRE, TERR, STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = (size_t)(kFwdScratch + (TIRE == TIRE_BEKKER ? kBekScratch : 0) + (MARGIN ? kNumMargins : 0)) * kFwdBlock * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(rollout_fwd_kernel<TIRE, TERR, STORE, MARGIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     e = upload_model(mc, d_live, s);
     if (e != cudaSuccess) return e;
-    rollout_fwd_kernel<TIRE, TERR, STORE><<<grid, kFwdBlock, smem, s>>>(a);
+    rollout_fwd_kernel<TIRE, TERR, STORE, MARGIN><<<grid, kFwdBlock, smem, s>>>(a);
     return cudaGetLastError();
 }
 

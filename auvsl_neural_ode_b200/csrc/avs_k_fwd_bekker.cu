@@ -10,6 +10,7 @@
 namespace avs {
 
 cudaError_t launch_fwd_bekker(const ModelConst& mc, const RolloutArgs& a, cudaStream_t s) {
+    if (a.margin) return launch_fwd_t<TIRE_BEKKER, TERR_DYN, false, true>(mc, nullptr, a, s);  // diagnostic: + branch margins
     return launch_fwd_t<TIRE_BEKKER, TERR_DYN, false>(mc, nullptr, a, s);
 }
 

@@ -36,6 +36,7 @@ struct RolloutArgs {
     const double* gt;
     double* loss;
     double* gps;
+    double* margin;  // [kNumMargins][N] branch margins (diagnostic Bekker rollout only) or nullptr
 };
 
 AVS_HD double ld(const double* p) {

@@ -9,6 +9,7 @@
 // light handle: creating many is cheap, and they are not thread-safe against each other (as include/avsim.h
 // says: one context per GPU, caller serialises).
 #pragma once
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <iostream>
@@ -46,7 +47,13 @@ public:
     }
     ~SharedContext() { avs_destroy(ctx); }
     avs_ctx* ctx = nullptr;
-    const void* terrain_owner = nullptr;  // which TerrainMap is currently loaded into the context
+    // which handle's terrain / parameters are currently loaded into the context.  Handle ids are drawn from a
+    // process-wide counter and never reused (an address would be: Trainer makes and destroys a System per trajectory)
+    unsigned long long terrain_owner = 0, params_owner = 0;
+    static unsigned long long nextHandleId() {
+        static std::atomic<unsigned long long> next{1};
+        return next.fetch_add(1);
+    }
 
 private:
     explicit SharedContext(int tire_model) {
@@ -61,7 +68,8 @@ public:
     typedef typename System<Scalar>::VectorS VectorS;
     typedef typename System<Scalar>::MatrixS MatrixS;
 
-    explicit GpuSystem(const std::shared_ptr<const TerrainMap<Scalar>>& map) : m_map(map), m_shared(SharedContext::get(TIRE)) {
+    explicit GpuSystem(const std::shared_ptr<const TerrainMap<Scalar>>& map)
+        : m_map(map), m_shared(SharedContext::get(TIRE)), m_id(SharedContext::nextHandleId()) {
         this->setNumParams(TIRE == AVS_TIRE_NN ? AVS_NUM_NN_PARAMS : AVS_NUM_BEKKER_PARAMS);
         this->setStateDim(AVS_STATE_DIM);
         this->setControlDim(AVS_CNTRL_DIM);
@@ -88,7 +96,6 @@ public:
         m_dirty = true;
     }
     void getParams(VectorS& params) override {
-        pull();
         params.resize(m_params.size());
         for (size_t i = 0; i < m_params.size(); i++) params[i] = m_params[i];
         if (TIRE == AVS_TIRE_BEKKER && params[3] < 0) params[3] = 0;  // BekkerDynamics::setParams clamp
@@ -170,7 +177,10 @@ public:
         if (TIRE != AVS_TIRE_NN) throw std::runtime_error("applyRmsProp: NN tire model only");
         bind();
         check(ctx(), avs_rmsprop_step(ctx(), reduced, lr, l1), "avs_rmsprop_step");
-        m_stale = true;
+        // the update ran on the device copy; fetch it at once (3.3 KB) so that the host copy of THIS handle stays the
+        // authoritative one: a later setParams(), or another handle re-binding the shared context, can then never
+        // lose or shadow the step
+        check(ctx(), avs_get_nn_params(ctx(), m_params.data()), "avs_get_nn_params");
     }
     avs_ctx* context() { bind(); return ctx(); }
 
@@ -181,14 +191,13 @@ private:
     avs_ctx* ctx() { return m_shared->ctx; }
     // push this system's parameters / terrain into the shared context if another handle touched it
     void bind() {
-        if (m_dirty || m_shared->terrain_owner != this) {
-            if (!m_stale) {
-                if (TIRE == AVS_TIRE_NN) check(ctx(), avs_set_nn_params(ctx(), m_params.data()), "avs_set_nn_params");
-                else check(ctx(), avs_set_bekker_params(ctx(), m_params.data()), "avs_set_bekker_params");
-            }
+        if (m_dirty || m_shared->params_owner != m_id) {
+            if (TIRE == AVS_TIRE_NN) check(ctx(), avs_set_nn_params(ctx(), m_params.data()), "avs_set_nn_params");
+            else check(ctx(), avs_set_bekker_params(ctx(), m_params.data()), "avs_set_bekker_params");
             m_dirty = false;
+            m_shared->params_owner = m_id;
         }
-        if (m_shared->terrain_owner != this) {
+        if (m_shared->terrain_owner != m_id) {
             const TerrainMap<Scalar>* map = m_map.get();
             const avs::TerrainKind k = map ? map->deviceKind() : avs::TERRAIN_FLAT;
             if (k == avs::TERRAIN_GRID) {
@@ -207,13 +216,7 @@ private:
             } else {
                 check(ctx(), avs_set_terrain_analytic(ctx(), (int)k), "avs_set_terrain_analytic");
             }
-            m_shared->terrain_owner = this;
-        }
-    }
-    void pull() {
-        if (m_stale && TIRE == AVS_TIRE_NN) {
-            check(ctx(), avs_get_nn_params(ctx(), m_params.data()), "avs_get_nn_params");
-            m_stale = false;
+            m_shared->terrain_owner = m_id;
         }
     }
     static int envInt(const char* k, int d) { const char* v = std::getenv(k); return v ? std::atoi(v) : d; }
@@ -222,8 +225,8 @@ private:
     std::shared_ptr<const TerrainMap<Scalar>> m_map;
     std::shared_ptr<SharedContext> m_shared;
     std::vector<double> m_params;
-    bool m_dirty = true;   // host copy newer than the context
-    bool m_stale = false;  // context (device RMSProp) newer than the host copy
+    const unsigned long long m_id;
+    bool m_dirty = true;  // host copy newer than the context
 };
 
 }  // namespace avs

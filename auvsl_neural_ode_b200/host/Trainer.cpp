@@ -2,6 +2,12 @@
 #include "Trainer.h"
 
 #include <cmath>
+#include <cstring>
+#include <stdexcept>
+#include <thread>
+
+#include "../../include/avsim.h"
+#include "TestTerrainMaps.h"
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -32,6 +38,8 @@ Trainer::Trainer(std::shared_ptr<SystemFactory<ADF>> factory, int num_threads) :
     m_data_dir = envOr("AVSL_DATA_DIR", "/home/justin/code/auvsl_dynamics_bptt/scripts/");
     if (!m_data_dir.empty() && m_data_dir.back() != '/') m_data_dir += '/';
     m_best_CV3 = .096;  // :72
+    const char* g = std::getenv("AVSL_GPUS");
+    m_gpus = g ? std::max(1, std::atoi(g)) : 1;
 }
 
 Trainer::~Trainer() {}
@@ -59,8 +67,10 @@ void Trainer::loadDataFile(std::string fn) {
     }
     std::string line;
     std::getline(f, line);  // column headings
+    bool last_row_terminated = false;
     while (std::getline(f, line)) {
-        if (line.empty()) continue;
+        const bool terminated = !f.eof();  // the line ended in '\n' (and not at the end of the file)
+        if (line.empty() || line.find_first_not_of(" \t\r") == std::string::npos) continue;
         for (char& c : line) if (c == ',') c = ' ';
         std::istringstream ss(line);
         double idx, wx, wy;
@@ -68,7 +78,13 @@ void Trainer::loadDataFile(std::string fn) {
         if (!(ss >> idx >> r.time >> r.vl >> r.vr >> r.x >> r.y >> r.yaw >> wx >> wy >> r.wz >> r.vx >> r.vy)) continue;
         r.z = m_z_stable;  // :138
         m_data.push_back(r);
+        last_row_terminated = terminated;
     }
+    // The reference loops on `while (data_file.peek() != EOF)` (:123): after the last row of a file that ends in a newline
+    // peek() still sees '\n', every extraction of the extra pass fails and leaves `row` untouched, and the LAST ROW IS PUSHED
+    // A SECOND TIME.  With the strict `j < size - window` bound of the window loops (:163, :353) that extra row decides
+    // whether a file of exactly k * stride + window rows yields its last window, so it is reproduced here.
+    if (last_row_terminated && !m_data.empty()) m_data.push_back(m_data.back());
 }
 
 std::string Trainer::dataFile(const char* stem, int idx) const {
@@ -84,18 +100,39 @@ std::vector<std::vector<GroundTruthDataRow>> Trainer::windowsOf(int window, int 
     return w;
 }
 
-// windows -> SoA buffers of include/avsim.h
-Trainer::Packed Trainer::pack(const std::vector<std::vector<GroundTruthDataRow>>& windows) {
+void Trainer::PinnedBuf::assignZero(size_t n) {
+    release();
+    if (n == 0) return;
+    void* p = nullptr;
+    if (avs_alloc_pinned(&p, (unsigned long long)(n * sizeof(double))) == AVS_OK) {
+        pinned_ = true;
+    } else {  // still host memory, only pageable: the copy engine stages it (not a compute fallback)
+        p = std::malloc(n * sizeof(double));
+        if (!p) throw std::bad_alloc();
+        pinned_ = false;
+    }
+    p_ = static_cast<double*>(p);
+    n_ = n;
+    std::memset(p_, 0, n * sizeof(double));
+}
+void Trainer::PinnedBuf::release() {
+    if (!p_) return;
+    if (pinned_) avs_free_pinned(p_); else std::free(p_);
+    p_ = nullptr; n_ = 0;
+}
+
+// windows [begin, end) -> SoA buffers of include/avsim.h, in page-locked memory
+Trainer::Packed Trainer::pack(const std::vector<std::vector<GroundTruthDataRow>>& windows, size_t begin, size_t end) {
     Packed p;
-    p.N = (int)windows.size();
-    if (p.N == 0) return p;
-    p.T = (int)windows[0].size();
+    p.N = (int)(end - begin);
+    if (p.N <= 0) { p.N = 0; return p; }
+    p.T = (int)windows[begin].size();
     const size_t N = p.N;
-    p.x0.assign(21 * N, 0.0);
-    p.ctrl.assign((size_t)(p.T - 1) * 2 * N, 0.0);
-    p.gt.assign((size_t)p.T * 3 * N, 0.0);
+    p.x0.assignZero(21 * N);
+    p.ctrl.assignZero((size_t)(p.T - 1) * 2 * N);
+    p.gt.assignZero((size_t)p.T * 3 * N);
     for (size_t n = 0; n < N; n++) {
-        const auto& tr = windows[n];
+        const auto& tr = windows[begin + n];
         VectorAD xk = m_system_adf->initializeState(tr[0]);  // :610
         for (int c = 0; c < 21; c++) p.x0[c * N + n] = xk[c];
         for (int i = 0; i < p.T; i++) {
@@ -179,8 +216,94 @@ void Trainer::train() {
     std::cout << "Average Loss: " << avg_loss / cnt_actual << "\n";
 }
 
+// ---- multi-GPU: one context + one host thread per GPU, ONE all-reduce per step behind the C ABI -----------------------
+struct Trainer::MultiGpu {
+    std::vector<avs_ctx*> ctx;
+    ~MultiGpu() { for (avs_ctx* c : ctx) avs_destroy(c); }
+};
+
+void Trainer::setNumGpus(int g) {
+    if (g < 1) g = 1;
+    if (g != m_gpus) m_multi.reset();
+    m_gpus = g;
+}
+
+static void ckAvs(avs_ctx* c, int rc, const char* what) {
+    if (rc != AVS_OK) throw std::runtime_error(std::string(what) + ": " + avs_strerror(rc) + " — " + (c ? avs_last_error(c) : "no context"));
+}
+
+double Trainer::trainBatchMultiGpu(const std::vector<std::vector<GroundTruthDataRow>>& windows, int explode_mode) {
+    const int G = m_gpus;
+    const int np = m_system_adf->getNumParams();
+    if (np != AVS_NUM_NN_PARAMS) throw std::runtime_error("Trainer: multi-GPU training exists for the NN tire model only");
+    if (!m_multi) {
+        auto mg = std::make_shared<MultiGpu>();
+        for (int g = 0; g < G; g++) {
+            avs_ctx* c = nullptr;
+            ckAvs(nullptr, avs_create(&c, g, AVS_TIRE_NN), "avs_create");
+            mg->ctx.push_back(c);
+        }
+        ckAvs(mg->ctx[0], avs_comm_init_all(mg->ctx.data(), G), "avs_comm_init_all");
+        // terrain: the factory's map, as the single-GPU systems configure it
+        const auto& map = m_factory_adf->terrainMap();
+        const avs::TerrainKind k = map ? map->deviceKind() : avs::TERRAIN_FLAT;
+        for (avs_ctx* c : mg->ctx) {
+            if (k == avs::TERRAIN_GRID) {
+                const avs::TerrainGrid* g = map->deviceGrid();
+                ckAvs(c, avs_set_terrain_grid(c, g->height.data(), g->soil.empty() ? nullptr : g->soil.data(), g->nx, g->ny, g->x0, g->y0, g->dx, g->dy), "avs_set_terrain_grid");
+            } else if (k == avs::TERRAIN_CUSTOM) {
+                throw std::runtime_error("Trainer: multi-GPU training needs a Flat/Slope/Bumpy/Grid terrain map");
+            } else {
+                ckAvs(c, avs_set_terrain_analytic(c, (int)k), "avs_set_terrain_analytic");
+            }
+        }
+        m_multi = mg;
+    }
+    const size_t N = windows.size();
+    std::vector<double> params(np);
+    for (int k = 0; k < np; k++) params[k] = m_params[k];
+    std::vector<std::vector<double>> red(G, std::vector<double>(AVS_REDUCED_LEN, 0.0));
+    std::vector<std::string> errs(G);
+    std::vector<Packed> shard(G);
+    for (int g = 0; g < G; g++) {  // contiguous shards, sizes differ by at most one (packing touches the shared System: serial)
+        const size_t base = N / G, rem = N % G;
+        const size_t b = g * base + std::min<size_t>(g, rem), e = b + base + ((size_t)g < rem ? 1 : 0);
+        shard[g] = pack(windows, b, e);
+    }
+    std::vector<std::thread> th;
+    for (int g = 0; g < G; g++) {
+        th.emplace_back([&, g]() {
+            try {
+                avs_ctx* c = m_multi->ctx[g];
+                ckAvs(c, avs_set_nn_params(c, params.data()), "avs_set_nn_params");
+                Packed& p = shard[g];
+                std::vector<double> loss(std::max(p.N, 1));
+                if (p.N > 0) {
+                    ckAvs(c, avs_rollout_grad(c, p.N, p.T, 10, p.x0.data(), p.ctrl.data(), p.gt.data(), 100.0, explode_mode, loss.data(), red[g].data(), nullptr),
+                          "avs_rollout_grad");
+                } else {  // a rank without windows still joins the collective with zeros
+                    ckAvs(c, avs_set_reduced(c, red[g].data()), "avs_set_reduced");
+                }
+                ckAvs(c, avs_allreduce(c, red[g].data()), "avs_allreduce");
+                // identical update on every replica (device RMSProp on the all-reduced buffer)
+                ckAvs(c, avs_rmsprop_step_dev(c, nullptr, m_lr, m_l1_weight), "avs_rmsprop_step_dev");
+                ckAvs(c, avs_sync(c), "avs_sync");
+            } catch (const std::exception& e) {
+                errs[g] = e.what();
+            }
+        });
+    }
+    for (auto& t : th) t.join();
+    for (int g = 0; g < G; g++) if (!errs[g].empty()) throw std::runtime_error("GPU " + std::to_string(g) + ": " + errs[g]);
+    m_cnt = (int)red[0][np + 1];
+    m_batch_loss = red[0][np];
+    for (int k = 0; k < np; k++) m_batch_grad[k] = red[0][k];
+    return m_cnt ? m_batch_loss / m_cnt : 0.0;
+}
+
 // one batched step over explicit windows (the GPU-shaped replacement of the worker pool, :204-305)
 double Trainer::trainBatch(const std::vector<std::vector<GroundTruthDataRow>>& windows, int explode_mode) {
+    if (m_gpus > 1) return trainBatchMultiGpu(windows, explode_mode);
     std::shared_ptr<System<ADF>> sys = m_system_adf;
     sys->setParams(m_params);
     Packed p = pack(windows);
@@ -206,7 +329,10 @@ void Trainer::trainThreads() {
     std::cout << "Avg Loss: " << avg << "\n";
     std::cout.flush();
     save();
-    if (m_cnt > 0) updateParams(m_batch_grad / m_cnt);
+    if (m_cnt > 0) {
+        if (m_gpus > 1) adoptDeviceUpdate();
+        else updateParams(m_batch_grad / m_cnt);
+    }
     if (avg < m_best_CV3 && m_cnt > 0) {
         m_best_CV3 = avg;
         std::cout << "dabest " << m_best_CV3 << "\n";
@@ -244,6 +370,27 @@ void Trainer::updateParams(const VectorF& grad) {
     std::cout << "Gradient norm: " << norm << " Param[0]: " << m_params[0] << " grad[0]: " << grad[0] << " update[0]: " << update0
               << " squared_grad[0]: " << std::sqrt(m_squared_grad[0]) << "\n";
     m_batch_grad = VectorF::Zero(m_system_adf->getNumParams());
+    m_system_adf->setParams(m_params);
+}
+
+// multi-GPU: every replica has already applied updateParams' RMSProp on its device copy (bit-identical across replicas);
+// fetch the result from replica 0 and print the reference's log line
+void Trainer::adoptDeviceUpdate() {
+    const int np = (int)m_params.size();
+    std::vector<double> p(np);
+    ckAvs(m_multi->ctx[0], avs_get_nn_params(m_multi->ctx[0], p.data()), "avs_get_nn_params");
+    double norm = 0;
+    for (int i = 0; i < np; i++) {
+        const double g = m_batch_grad[i] / m_cnt;
+        const float gf = (float)g;
+        m_squared_grad[i] = 0.95 * m_squared_grad[i] + 0.05 * (double)(gf * gf);
+        norm += std::fabs(g);
+        m_params[i] = p[i];
+    }
+    const double g0 = m_batch_grad[0] / m_cnt;
+    std::cout << "Gradient norm: " << norm << " Param[0]: " << m_params[0] << " grad[0]: " << g0 << " update[0]: "
+              << (m_lr / (std::sqrt(m_squared_grad[0]) + 1e-6)) * g0 << " squared_grad[0]: " << std::sqrt(m_squared_grad[0]) << "\n";
+    m_batch_grad = VectorF::Zero(np);
     m_system_adf->setParams(m_params);
 }
 

@@ -54,6 +54,12 @@ public:
     std::vector<double> evaluateWindows(int window, int stride);
     // one full-batch training step over explicit windows; returns the mean kept loss
     double trainBatch(const std::vector<std::vector<GroundTruthDataRow>>& windows, int explode_mode);
+    // number of GPUs trainBatch / trainThreads shard the batch over (default: AVSL_GPUS or 1).  With G > 1 the Trainer owns
+    // one context per GPU, one host thread per context, and ONE ncclAllReduce of the 418 reduced doubles per step behind
+    // the C ABI (avs_allreduce); every replica then applies the same device RMSProp (reference seam: src/Trainer.cpp:204-263,
+    // 661-689 — worker threads + `batch_grad += sample_grad` on the main thread)
+    void setNumGpus(int g);
+    int numGpus() const { return m_gpus; }
     void setDataDir(const std::string& d) { m_data_dir = d; }
     void setParamFile(const std::string& f) { m_param_file = f; }
 
@@ -80,8 +86,35 @@ public:
     const int m_num_threads;
 
 private:
-    struct Packed { int N = 0, T = 0; std::vector<double> x0, ctrl, gt; };
-    Packed pack(const std::vector<std::vector<GroundTruthDataRow>>& windows);
+    // page-locked staging buffer (cudaHostAlloc through avs_alloc_pinned): the SoA batches go to the GPU by DMA
+    class PinnedBuf {
+    public:
+        PinnedBuf() = default;
+        PinnedBuf(const PinnedBuf&) = delete;
+        PinnedBuf& operator=(const PinnedBuf&) = delete;
+        PinnedBuf(PinnedBuf&& o) noexcept : p_(o.p_), n_(o.n_), pinned_(o.pinned_) { o.p_ = nullptr; o.n_ = 0; }
+        PinnedBuf& operator=(PinnedBuf&& o) noexcept { if (this != &o) { release(); p_ = o.p_; n_ = o.n_; pinned_ = o.pinned_; o.p_ = nullptr; o.n_ = 0; } return *this; }
+        ~PinnedBuf() { release(); }
+        void assignZero(size_t n);
+        double* data() { return p_; }
+        const double* data() const { return p_; }
+        double& operator[](size_t i) { return p_[i]; }
+        size_t size() const { return n_; }
+        bool pinned() const { return pinned_; }
+    private:
+        void release();
+        double* p_ = nullptr;
+        size_t n_ = 0;
+        bool pinned_ = false;
+    };
+    struct Packed { int N = 0, T = 0; PinnedBuf x0, ctrl, gt; };
+    Packed pack(const std::vector<std::vector<GroundTruthDataRow>>& windows) { return pack(windows, 0, windows.size()); }
+    Packed pack(const std::vector<std::vector<GroundTruthDataRow>>& windows, size_t begin, size_t end);
+    struct MultiGpu;
+    std::shared_ptr<MultiGpu> m_multi;
+    int m_gpus = 1;
+    void adoptDeviceUpdate();
+    double trainBatchMultiGpu(const std::vector<std::vector<GroundTruthDataRow>>& windows, int explode_mode);
     std::vector<std::vector<GroundTruthDataRow>> windowsOf(int window, int stride) const;
     std::string dataFile(const char* stem, int idx) const;
     void evaluateSet(const char* stem, int first, int last, const char* label, bool per_window_lines);

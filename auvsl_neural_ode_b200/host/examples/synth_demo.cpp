@@ -3,6 +3,7 @@
 // the same calls as the reference's evaluate.cpp and train.cpp (trainThreads + train) against them.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <fstream>
 #include <iostream>
 #include <random>
@@ -33,8 +34,14 @@ static void writeCsv(const std::string& fn, int rows, unsigned seed) {
     }
 }
 
+// usage: synth_demo [dir] [--gpus G]    (G > 1: trainThreads shards the batch over G GPUs, one all-reduce per step)
 int main(int argc, char** argv) {
-    const std::string dir = argc > 1 ? argv[1] : "/tmp/avsl_synth/";
+    std::string dir = "/tmp/avsl_synth/";
+    int gpus = 0;
+    for (int i = 1; i < argc; i++) {
+        if (std::string(argv[i]) == "--gpus" && i + 1 < argc) gpus = std::atoi(argv[++i]);
+        else dir = argv[i];
+    }
     char buf[256];
     std::snprintf(buf, sizeof(buf), "mkdir -p %s", dir.c_str());
     if (std::system(buf) != 0) return 2;
@@ -45,6 +52,8 @@ int main(int argc, char** argv) {
     auto map = std::make_shared<const FlatTerrainMap<ADF>>();
     auto factory = std::make_shared<VehicleSystemFactory<ADF>>(map);
     Trainer train(factory, 2);
+    if (gpus > 0) train.setNumGpus(gpus);
+    std::cout << "GPUs: " << train.numGpus() << "\n";
     train.setDataDir(dir);
     train.setParamFile(dir + "tire.net");
     train.load();
@@ -55,6 +64,12 @@ int main(int argc, char** argv) {
         train.evaluate_validation_dataset();
     }
     train.save();
+    {   // order-independent fingerprint of the trained parameters (compared across --gpus settings and against the Python path)
+        std::cout.precision(17);
+        double sum = 0, wsum = 0;
+        for (size_t i = 0; i < train.m_params.size(); i++) { sum += train.m_params[i]; wsum += (double)(i + 1) * train.m_params[i]; }
+        std::cout << "params sum " << sum << " weighted " << wsum << " p[0] " << train.m_params[0] << " p[103] " << train.m_params[103] << "\n";
+    }
     std::cout << "synth_demo OK\n";
     return 0;
 }

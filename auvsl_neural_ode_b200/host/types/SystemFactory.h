@@ -10,6 +10,7 @@ public:
     explicit SystemFactory(const MapPtr& map) : m_terrain_map{map} {}
     virtual ~SystemFactory() = default;
     virtual std::shared_ptr<System<Scalar>> makeSystem() = 0;
+    const MapPtr& terrainMap() const { return m_terrain_map; }  // extension: the multi-GPU Trainer configures one context per GPU
 
 protected:
     const MapPtr m_terrain_map;

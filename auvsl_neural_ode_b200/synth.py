@@ -8,9 +8,16 @@ velocities from the same model.
 """
 import numpy as np
 
-from . import capi
+# NOTE: no import of .capi here — bench.py's reference arm builds its inputs with this module and must not map libavsim.so.
 
 SEED = 20231115
+# whole-body COM (generated/miscellaneous.cpp:6-39 with model_constants.h:24-100; wheel COMs are the joint origins, whose x and
+# y offsets cancel over the four wheels) and the Bekker soil defaults (src/BekkerSystem.cpp:21-28)
+_M_BASE, _M_WHEEL = 16.52400016784668, 0.47699999809265137
+_COM_BASE = np.array([0.011999273672699928, 0.0, 0.06699594855308533])
+_TZ_WHEEL = 0.03449999913573265
+WHOLE_BODY_COM = (_COM_BASE * _M_BASE + np.array([0.0, 0.0, 4 * _M_WHEEL * _TZ_WHEEL])) / (_M_BASE + 4 * _M_WHEEL)
+BEKKER_DEFAULT = np.array([.2976, 2.083, 0.8, 0.0, .3927])
 B = np.array([[0.0472, 0.0438], [0.0036, -0.0035], [-0.1744, 0.1748]])  # gen_fake_data.py:8-10
 Z_STABLE_NN = 0.0584427891  # HybridDynamics::settle with the default NN weights on flat ground
 
@@ -45,7 +52,7 @@ def make_batch(N, T, seed=SEED, z_stable=Z_STABLE_NN, rate_hz=100.0):
         gt[i, 0], gt[i, 1], gt[i, 2] = yaw, x, y
 
     v0 = B @ np.stack([vl[0], vr[0]])
-    com = capi.whole_body_com()
+    com = WHOLE_BODY_COM
     x0 = np.zeros((21, N))
     x0[2], x0[3] = np.sin(yaw0 / 2.0), np.cos(yaw0 / 2.0)
     x0[6] = z_stable
@@ -72,7 +79,7 @@ def make_grid_terrain(seed=SEED, n=512, cell=0.05, with_soil=True):
     h = sum(A[k] * np.sin(kx[k] * X + ky[k] * Y + ph[k]) for k in range(8))
     soil = None
     if with_soil:
-        d = capi.bekker_default_params()
+        d = BEKKER_DEFAULT
         soil = np.empty((5, n, n))
         for k in (0, 1, 2, 4):
             soil[k] = d[k] * rng.uniform(0.8, 1.2, (n, n))

@@ -41,7 +41,8 @@ enum {
     AVS_E_ARG = 1,    /* invalid argument */
     AVS_E_CUDA = 2,   /* CUDA runtime error / no usable device */
     AVS_E_STATE = 3,  /* call not valid for the configured tire model / terrain */
-    AVS_E_NOMEM = 4
+    AVS_E_NOMEM = 4,
+    AVS_E_COMM = 5    /* NCCL error / communicator missing */
 };
 
 enum { AVS_TIRE_NN = 0, AVS_TIRE_BEKKER = 1 };
@@ -53,6 +54,8 @@ enum { AVS_EXPLODE_ZERO_COMPONENT = 0, AVS_EXPLODE_DROP_SAMPLE = 1 };
 #define AVS_NUM_NN_PARAMS 416
 #define AVS_NUM_BEKKER_PARAMS 5
 #define AVS_REDUCED_LEN 418 /* grad_sum[416] | loss_sum | n_kept */
+#define AVS_NUM_MARGINS 6   /* branch-margin kinds of the Bekker path, see avs_rollout_margins */
+#define AVS_COMM_ID_BYTES 128
 
 /* ---- life cycle.  Replaces: `new HybridDynamics` / `makeSystem()` per trajectory
  *      (src/Trainer.cpp:596, src/VehicleSystem.h:38-51, src/BekkerSystem.h factory). */
@@ -103,6 +106,19 @@ int avs_ode(avs_ctx* ctx, int N, const double* x, const double* u, double* xd);
 int avs_rollout(avs_ctx* ctx, int N, int T, int substeps, const double* x0, const double* ctrl, double* x_list, double* x_final);
 int avs_rollout_dev(avs_ctx* ctx, int N, int T, int substeps, const double* d_x0, const double* d_ctrl, double* d_x_list, double* d_x_final);
 
+/* ---- diagnostic forward rollout of the Bekker model that also reports, per trajectory, how far every value-dependent
+ *      branch of BekkerDynamics::get_tire_f_ext / BekkerTireModel::{get_features, get_forces, integrate} stayed from flipping
+ *      (minimum over all ODE evaluations of the rollout).  margins [6][N]:
+ *        0 |sinkage|                      contact on/off            (BekkerDynamics.cpp:81)
+ *        1 |w R - vx|                     sign of Fx                (BekkerDynamics.cpp:93)
+ *        2 ||vx| - 1e-3|, ||w R| - 1e-3|  slip clamps               (BekkerTireModel.cpp:197-198)
+ *        3 |pgc - pg| / pg                ground-pressure branch    (BekkerTireModel.cpp:232)
+ *        4 |R - sinkage|                  zr = min(zr, R)           (BekkerTireModel.cpp:219)
+ *        5 |dtheta| of non-empty arcs     trapezoid loop bound      (BekkerTireModel.cpp:166-170)
+ *      Two correct implementations may differ by O(1e-3) on a trajectory whose margin is within rounding of 0; parity
+ *      tests gate on margin > 1e-10 and report the rest.  Tire model must be AVS_TIRE_BEKKER. */
+int avs_rollout_margins(avs_ctx* ctx, int N, int T, int substeps, const double* x0, const double* ctrl, double* x_list, double* x_final, double* margins);
+
 /* ---- forward + reverse (BPTT).  Replaces Trainer::trainTrajectory (src/Trainer.cpp:591-659: CppAD
  *      tape + ADFun::Reverse(1)) for N windows at once, plus the per-sample explosion filter and sum of
  *      Trainer::train (:169-193, mode 0: zero the exploding component) or Trainer::combineResults
@@ -120,10 +136,39 @@ int avs_rollout_grad_dev(avs_ctx* ctx, int N, int T, int substeps, const double*
 /* ---- Trainer::updateParams (src/Trainer.cpp:428-453): RMSProp on the context's NN parameters with the
  *      float-truncated gradient g = reduced[0..415] / reduced[417].  d_reduced is a DEVICE pointer
  *      (typically the all-reduced buffer); squared-gradient state lives in the context (starts at 1). */
-int avs_rmsprop_step_dev(avs_ctx* ctx, const double* d_reduced, double lr, double l1_weight);
+int avs_rmsprop_step_dev(avs_ctx* ctx, const double* d_reduced /* NULL = the context's own reduced buffer */, double lr, double l1_weight);
 /* host variant: uploads reduced[418] first (e.g. after a host-side reduction over ranks) */
 int avs_rmsprop_step(avs_ctx* ctx, const double* reduced_host, double lr, double l1_weight);
+/* upload reduced[418] into the context's own reduced buffer (e.g. zeros on a rank whose shard is empty, before avs_allreduce) */
+int avs_set_reduced(avs_ctx* ctx, const double* reduced_host);
+/* squared-gradient state back to ones (m_squared_grad = Ones, src/Trainer.cpp:63); the parameters are not touched */
 int avs_reset_optimizer(avs_ctx* ctx);
+
+/* ---- multi-GPU.  Replaces the gradient seam of the reference's worker pool (src/Trainer.cpp:204-263 trainThreads,
+ *      :661-689 combineResults: `batch_grad += sample_grad` on the main thread): the batch is sharded by trajectory, one
+ *      context (= one NCCL rank) per GPU; each rank filters and sums its shard on the device, then ONE ncclAllReduce(sum) of
+ *      reduced[418] (grad_sum | loss_sum | n_kept) runs in place on the context's stream, and every rank applies the same
+ *      RMSProp update, so the replicas stay bit-identical without a broadcast.  NCCL is bound at run time (dlopen of
+ *      libnccl.so.2); these calls fail with AVS_E_COMM when it is absent.
+ *        one process per GPU : rank 0 calls avs_comm_unique_id and ships the 128 bytes to the other ranks (any transport);
+ *                              every rank calls avs_comm_init_rank
+ *        one process, n GPUs : avs_comm_init_all over n contexts on n distinct devices; then one host thread per context */
+int avs_comm_unique_id(char* id128);
+int avs_comm_init_rank(avs_ctx* ctx, const char* id128, int world, int rank);
+int avs_comm_init_all(avs_ctx** ctxs, int n);
+int avs_comm_destroy(avs_ctx* ctx);
+int avs_comm_info(const avs_ctx* ctx, int* world, int* rank, int* nccl_version);
+/* in-place all-reduce of a DEVICE buffer of 418 doubles (NULL = the context's own reduced buffer, i.e. what the host-buffer
+ * avs_rollout_grad left on the device); enqueued on the context's stream, no synchronisation, no host hop.  A context
+ * without a communicator and world == 1 returns AVS_OK without doing anything. */
+int avs_allreduce_dev(avs_ctx* ctx, double* d_reduced);
+/* host convenience: all-reduce the context's own reduced buffer and (optionally) copy the result to reduced_host_out[418] */
+int avs_allreduce(avs_ctx* ctx, double* reduced_host_out);
+
+/* ---- pinned (page-locked) host staging for the SoA buffers of the host-pointer entry points
+ *      (Trainer::loadDataFile -> windows -> x0 / ctrl / gt, reference src/Trainer.cpp:102-143, 163-165) */
+int avs_alloc_pinned(void** out, unsigned long long bytes);
+int avs_free_pinned(void* p);
 
 /* ---- stream / bookkeeping */
 void* avs_stream(avs_ctx* ctx);                 /* cudaStream_t the *_dev calls are enqueued on */

@@ -275,6 +275,25 @@ template <class S> struct TireNetwork {
 };
 
 // ---------------------------------------------------------------------------------------------
+// Branch-margin probe (SURVEY.md §7 "parity hazards from discontinuities").  The Bekker path switches on values:
+// a predicate that sits within rounding distance of its threshold may flip between two correct implementations and
+// change the result by O(1e-3).  When a probe array is installed (thread-local), every evaluation records how far each
+// predicate was from flipping; the minimum over a rollout is the trajectory's branch margin.  Kinds:
+//   0 |sinkage|                       contact on/off                 BekkerDynamics.cpp:81
+//   1 |w R - vx|                      sign of Fx                     BekkerDynamics.cpp:93
+//   2 ||vx| - 1e-3|, ||w R| - 1e-3|   slip clamps                    BekkerTireModel.cpp:197-198
+//   3 |pgc - pg| / pg                 ze = zr  vs  (pg/k)^(1/n)      BekkerTireModel.cpp:232
+//   4 |R - sinkage|                   zr = min(zr, R)                BekkerTireModel.cpp:219
+//   5 |dtheta| of non-empty arcs      trapezoid loop bound           BekkerTireModel.cpp:166-170
+// ---------------------------------------------------------------------------------------------
+constexpr int NUM_MARGINS = 6;
+inline double*& active_margin() { static thread_local double* p = nullptr; return p; }
+inline void margin_note(int kind, double v) {
+    double* m = active_margin();
+    if (m && v < m[kind]) m[kind] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
 // BekkerTireModel: include/auvsl_dynamics/BekkerTireModel.h, src/auvsl_dynamics/BekkerTireModel.cpp
 // ---------------------------------------------------------------------------------------------
 template <class S> struct BekkerTireModel {
@@ -317,6 +336,7 @@ template <class S> struct BekkerTireModel {
     S integrate(Fn func, S upper_b, S lower_b) {
         S dtheta = (upper_b - lower_b) / (double)num_steps;
         S eps = dtheta * .1;
+        if (value(dtheta) != 0.0) margin_note(5, std::fabs(value(dtheta)));
         S sum(0.0);
         for (S theta = lower_b; theta < (upper_b - eps - dtheta); theta += dtheta) {
             sum += .5 * dtheta * ((this->*func)(theta + dtheta) + (this->*func)(theta));
@@ -328,6 +348,8 @@ template <class S> struct BekkerTireModel {
     void get_features(const S inputs[4], S out[3]) {
         S tire_vx = inputs[1], tire_vy = inputs[2], w_R = inputs[3];
         const S small(1e-3);
+        margin_note(2, std::fabs(std::fabs(value(tire_vx)) - 1e-3));
+        margin_note(2, std::fabs(std::fabs(value(w_R)) - 1e-3));
         S tire_vx_clamped = cond_gt(s_abs(tire_vx), small, tire_vx, small);
         S tangent_vx_clamped = cond_gt(s_abs(w_R), small, w_R, small);
         S sr = 1 - (tire_vx_clamped / tangent_vx_clamped);
@@ -336,12 +358,14 @@ template <class S> struct BekkerTireModel {
     }
     // :212-278
     void get_forces(const S features[8], S wrench[4]) {
+        margin_note(4, std::fabs(R - value(features[0])));
         zr = cond_gt(features[0], S(R), S(R), features[0]);
         slip_ratio = features[1];
         slip_angle = features[2];
         kc = features[3]; kphi = features[4]; n0 = features[5]; n1 = features[6]; phi = features[7];
         n = n0 + (n1 * s_abs(slip_ratio));
         pgc = ((kc / b) + kphi) * s_pow(zr, n);
+        margin_note(3, std::fabs(value(pgc) - pg) / pg);
         if (value(pgc) < pg) {
             ze = zr;
         } else {
@@ -638,6 +662,8 @@ template <class S> struct HybridDynamics {
                 inputs[0] = sinkages[ii]; inputs[1] = tire_vx; inputs[2] = cpt_vels[ii][1]; inputs[3] = vel_x_tan;
                 bekker_tire_model.get_features(inputs, bf);
                 features[0] = bf[0]; features[1] = bf[1]; features[2] = bf[2];
+                margin_note(0, std::fabs(value(sinkages[ii])));
+                margin_note(1, std::fabs(value(vel_x_tan) - value(cpt_vels[ii][0])));
                 if (value(sinkages[ii]) > 0.0) {
                     bekker_tire_model.get_forces(features, forces);
                 } else {

@@ -321,6 +321,36 @@ void orc_rollout_grad_batch(const double* p416, const orc_terrain* t, int N, int
     }
 }
 
+// forward rollouts that also report the branch margins (jackal_oracle.hpp): margins [NUM_MARGINS][N] = per trajectory the
+// minimum over every ODE evaluation of the rollout
+void orc_rollout_batch_margins(int tire_model, const double* params, const orc_terrain* t, int N, int T, int substeps, const double* x0,
+                               const double* ctrl, double* x_list, double* x_final, double* margins, int nthreads) {
+    TerrainSpec terr = mkTerrain(t);
+    parallelFor(N, nthreads, [&](int n) {
+        double m[NUM_MARGINS];
+        for (int k = 0; k < NUM_MARGINS; k++) m[k] = 1e300;
+        active_margin() = m;
+        VehicleSystem<double> sys(tire_model, terr);
+        sys.substeps = substeps;
+        sys.setParams(params);
+        double xk[23], xk1[23];
+        for (int k = 0; k < 21; k++) xk[k] = x0[(size_t)k * N + n];
+        xk[21] = T > 1 ? ctrl[(size_t)0 * N + n] : 0.0;
+        xk[22] = T > 1 ? ctrl[(size_t)1 * N + n] : 0.0;
+        if (x_list) for (int k = 0; k < 23; k++) x_list[((size_t)0 * 23 + k) * N + n] = xk[k];
+        for (int i = 1; i < T; i++) {
+            xk[21] = ctrl[((size_t)(i - 1) * 2 + 0) * N + n];
+            xk[22] = ctrl[((size_t)(i - 1) * 2 + 1) * N + n];
+            sys.integrate(xk, xk1);
+            for (int k = 0; k < 23; k++) xk[k] = xk1[k];
+            if (x_list) for (int k = 0; k < 23; k++) x_list[((size_t)i * 23 + k) * N + n] = xk[k];
+        }
+        if (x_final) for (int k = 0; k < 21; k++) x_final[(size_t)k * N + n] = xk[k];
+        active_margin() = nullptr;
+        for (int k = 0; k < NUM_MARGINS; k++) margins[(size_t)k * N + n] = m[k];
+    });
+}
+
 int orc_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
 
 }  // extern "C"

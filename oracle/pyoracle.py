@@ -238,6 +238,22 @@ def rollout_batch(model, params, t, x0, ctrl, T, substeps=10, want_list=True, nt
     return xl, xf
 
 
+MARGIN_KINDS = ("contact |sinkage|", "Fx sign |wR - vx|", "slip clamps", "|pgc - pg| / pg", "|R - sinkage|", "arc |dtheta|")
+
+
+def rollout_batch_margins(model, params, t, x0, ctrl, T, substeps=10, want_list=True, nthreads=1):
+    """rollout_batch + margins [6][N]: how far every value-dependent branch of the Bekker path stayed from flipping
+    (minimum over the rollout; kinds in MARGIN_KINDS, definitions in jackal_oracle.hpp)"""
+    params, x0, ctrl = _f64(params), _f64(x0), _f64(ctrl)
+    N = x0.shape[1]
+    xl = np.zeros((T, 23, N)) if want_list else None
+    xf = np.zeros((21, N))
+    mg = np.zeros((6, N))
+    lib().orc_rollout_batch_margins(model, _p(params), C.byref(t), N, T, substeps, _p(x0), _p(ctrl),
+                                    _p(xl) if want_list else None, _p(xf), _p(mg), nthreads)
+    return xl, xf, mg
+
+
 def rollout_grad_batch(p416, t, x0, ctrl, gt, T, explode_thresh=100.0, explode_mode=0, nthreads=1, per_sample=True):
     """gt [T][3][N] (yaw,x,y) -> loss[N], grad_sum[416], loss_sum, n_kept, grad_per_sample[416][N]"""
     p416, x0, ctrl, gt = _f64(p416), _f64(x0), _f64(ctrl), _f64(gt)

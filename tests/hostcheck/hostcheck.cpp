@@ -82,6 +82,31 @@ template <int TIRE, int TERR> static void fwd_body(const ModelConst& mc, const R
         rollout_fwd_body<false>(a, n, 0, true, Scratch<1>{sc}, mk);
     }
 }
+// Bekker rollout with the branch-margin probe (avs_bekker.cuh): same node evaluation as BekNodesInline + a minima sink
+struct BekNodesMarginHost {
+    double* m;
+    void margin(int kind, double v) const { if (v < m[kind]) m[kind] = v; }
+    void operator()(const BekNodeParams& q, const double* th, const double* s, const double* c, double* fx, double* fy, double* fz) const {
+        BekNodesInline()(q, th, s, c, fx, fy, fz);
+    }
+};
+template <int TERR> struct OdeFwdMarginHost {
+    const ModelConst& mc; double ul, ur; double* m;
+    double* act_step = nullptr;  // (member GenericStep expects; the STORE path is never instantiated for it)
+    template <class St> void operator()(St T, St K, int) const {
+        double X[13], Xd[13];
+        for (int c = 0; c < 13; c++) X[c] = T[c];
+        ode_fwd<4, 1, TERR, false, BekNodesMarginHost>(mc, 0, X, ul, ur, Xd, nullptr, ActOutPtr{nullptr}, BekNodesMarginHost{m});
+        for (int c = 0; c < 13; c++) K[c] = Xd[c];
+    }
+};
+template <int TIRE, int TERR> static void fwd_body_margin(const ModelConst& mc, const RolloutArgs& a, int n, double* m) {
+    double sc[kFwdScratch];
+    typedef OdeFwdMarginHost<TERR> Ode;
+    auto mk = [&](double ul, double ur) { return GenericStep<false, Ode, Scratch<1>>{Ode{mc, ul, ur, m}, a, n, 0, true, Scratch<1>{sc}}; };
+    rollout_fwd_body<false>(a, n, 0, true, Scratch<1>{sc}, mk);
+}
+
 template <int TERR> static void bwd_body(const ModelConst& mc, const RolloutArgs& a, int n, HostAcc& acc, double& loss) {
     double sc[kBwdScratch];
     auto mk = [&mc, &acc](double ul, double ur) { return OdeBwdInline<4, TERR, HostAcc>{mc, 0, ul, ur, acc}; };
@@ -168,6 +193,18 @@ void hc_rollout(const hc_model* m, int N, int T, int substeps, const double* x0,
     RolloutArgs a; memset(&a, 0, sizeof(a));
     a.N = N; a.Nc = N; a.T = T; a.substeps = substeps; a.x0 = x0; a.ctrl = ctrl; a.x_list = x_list; a.x_final = x_final;
     for (int n = 0; n < N; n++) DISPATCH(fwd_body, m->tire, m->terr, mc, a, n, false);
+}
+// Bekker rollout + branch margins [kNumMargins][N] (same definitions as the kernel's diagnostic instantiation)
+void hc_rollout_margins(const hc_model* m, int N, int T, int substeps, const double* x0, const double* ctrl, double* x_list, double* x_final, double* margins) {
+    ModelConst mc; mk(m, mc);
+    RolloutArgs a; memset(&a, 0, sizeof(a));
+    a.N = N; a.Nc = N; a.T = T; a.substeps = substeps; a.x0 = x0; a.ctrl = ctrl; a.x_list = x_list; a.x_final = x_final;
+    for (int n = 0; n < N; n++) {
+        double mm[kNumMargins];
+        for (int k = 0; k < kNumMargins; k++) mm[k] = 1e300;
+        DISPATCH(fwd_body_margin, 1, m->terr, mc, a, n, mm);
+        for (int k = 0; k < kNumMargins; k++) margins[(size_t)k * N + n] = mm[k];
+    }
 }
 void hc_rollout_grad(const hc_model* m, int N, int T, int substeps, const double* x0, const double* ctrl, const double* gt, double* loss, double* gps104xN) {
     ModelConst mc; mk(m, mc);

@@ -116,6 +116,14 @@ def rollout(m, x0, ctrl, T, substeps=10, want_list=True):
     return xl, xf
 
 
+def rollout_margins(m, x0, ctrl, T, substeps=10):
+    x0, ctrl = _f64(x0), _f64(ctrl)
+    N = x0.shape[1]
+    xl, xf, mg = np.zeros((T, 23, N)), np.zeros((21, N)), np.zeros((6, N))
+    lib().hc_rollout_margins(C.byref(m), N, T, substeps, _p(x0), _p(ctrl), _p(xl), _p(xf), _p(mg))
+    return xl, xf, mg
+
+
 def rollout_grad(m, x0, ctrl, gt, T, substeps=10):
     x0, ctrl, gt = _f64(x0), _f64(ctrl), _f64(gt)
     N = x0.shape[1]

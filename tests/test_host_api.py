@@ -41,7 +41,7 @@ def test_synth_demo_runs_and_matches_python_path(tmp_path):
     rows_all = []
     for i in range(1, 17):
         a = np.loadtxt(os.path.join(d, f"Train3_data{i:02d}.csv"), delimiter=",", skiprows=1)
-        for j in range(0, a.shape[0] - 200, 200):
+        for j in range(0, a.shape[0] + 1 - 200, 200):  # + 1: the loader's duplicated last row (reference Trainer.cpp:123)
             rows_all.append(a[j:j + 200])
     N, T = len(rows_all), 200
     ctx = capi.Context(0, capi.TIRE_NN)
@@ -91,7 +91,9 @@ def test_reference_evaluate_mains_run_unchanged_and_match_oracle(tmp_path, main,
     logs = {"LD3_data01.csv": _write_log(d + "LD3_data01.csv", 1900, 5)}
     for i in (1, 2, 17):
         logs[f"Train3_data{i:02d}.csv"] = _write_log(d + f"Train3_data{i:02d}.csv", 1300, 40 + i)
-    logs["CV3_data01.csv"] = _write_log(d + "CV3_data01.csv", 1250, 90)
+    # exactly 2 x 600 rows: the reference's loader pushes the last row twice when the file ends in a newline
+    # (`while (peek() != EOF)`, Trainer.cpp:123), so the strict `j < size - window` bound (:353) still yields BOTH windows
+    logs["CV3_data01.csv"] = _write_log(d + "CV3_data01.csv", 1200, 90)
     env = dict(os.environ, AVSL_DATA_DIR=d, AVSL_PARAM_FILE=d + "none.net")
     out = subprocess.run([exe], capture_output=True, text=True, timeout=900, env=env)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
@@ -101,7 +103,7 @@ def test_reference_evaluate_mains_run_unchanged_and_match_oracle(tmp_path, main,
 
     def oracle_losses(a):
         res = []
-        for j in range(0, a.shape[0] - 600, 600):
+        for j in range(0, a.shape[0] + 1 - 600, 600):
             w = a[j:j + 600]
             rows = np.stack([w[:, 1], w[:, 2], w[:, 3], w[:, 4], w[:, 5], np.full(600, z), w[:, 6], w[:, 9], w[:, 10], w[:, 11]], axis=1)
             res.append(po.evaluate_trajectory(model, params, flat, rows)[0])
@@ -111,6 +113,7 @@ def test_reference_evaluate_mains_run_unchanged_and_match_oracle(tmp_path, main,
     ld3 = float(re.search(r"LD3 avg loss: ([-+0-9.eE]+)", out.stdout).group(1))
     assert ld3 == pytest.approx(np.mean(oracle_losses(logs["LD3_data01.csv"])), rel=tol)
     cv3 = [float(x) for x in re.findall(r"CV3 \d+ loss: ([-+0-9.eE]+)", out.stdout)]
+    assert len(cv3) == 2
     assert cv3 == pytest.approx(oracle_losses(logs["CV3_data01.csv"]), rel=tol)
     tr3 = float(re.search(r"Train3 avg loss: ([-+0-9.eE]+)", out.stdout).group(1))
     want = [l for i in (1, 2, 17) for l in oracle_losses(logs[f"Train3_data{i:02d}.csv"])]
