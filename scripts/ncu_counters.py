@@ -45,6 +45,8 @@ for r in data:
         continue
     steps = float(manifest[tag])
     dfma = val(r, "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum")
+    if dfma is None or dfma != dfma:  # an interrupted replay leaves NaNs: keep the previous (complete) launch of the family
+        continue
     dmul = val(r, "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum")
     dadd = val(r, "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum")
     k = {
