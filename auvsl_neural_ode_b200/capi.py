@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libavsim.so")
+# AVS_LIB selects another build of the same library (development: A/B timing of kernel variants, the AVS_DEBUG build)
+LIB_PATH = os.environ.get("AVS_LIB") or os.path.join(_HERE, "libavsim.so")
 
 TIRE_NN, TIRE_BEKKER = 0, 1
 FLAT, SLOPE, BUMPY, GRID = 0, 1, 2, 3

@@ -460,7 +460,7 @@ static int rollout_grad_impl(avs_ctx* ctx, int N, int T, int substeps, const dou
         }
         chunk = budget / per_vehicle;
         if (chunk >= n) chunk = n;
-        else chunk = (chunk / 256) * 256;  // whole CTAs
+        else chunk = (chunk / 256) * 256;  // whole CTAs (aligning chunks to whole resident waves was measured: no gain, round 2)
         ctx->plan_N = N; ctx->plan_per_vehicle = per_vehicle; ctx->plan_budget = ctx->ckpt_budget; ctx->plan_chunk = chunk;
     }
     if (chunk == 0) return fail(ctx, AVS_E_NOMEM, "avs_rollout_grad: the reverse-sweep buffers of one 256-vehicle chunk (%zu B) exceed the memory budget", per_vehicle * 256);

@@ -88,9 +88,11 @@ template <int TIRE, int TERR, int BLOCK, bool STORE_ACT, bool MARGIN = false> st
 // ---- fused forward stage (NN kernels): one non-inlined call = store the stage record, evaluate K = f(T), and apply the
 // RK4 stage update of HybridDynamics.cpp:470-500 (same arithmetic and order as rk4_fwd in avs_model.cuh), so that the
 // rolled loop in the kernel contains nothing but four calls.  Scratch slots: X 0 | ACC 13 | T 26 | INV 56.
+// tid = threadIdx.x, handed in by the caller: the non-inlined callee would otherwise re-read the special register (S2R, a
+// short-scoreboard wait at the head of every call: forward+store 11.25 -> 11.06 ms, round 2)
 template <int TERR, int BLOCK, bool STORE>
-__device__ __noinline__ void ode_fwd_stage_call(int lane0, double ul, double ur, int s, double* rec, double* act) {
-    const Scratch<BLOCK> X = scratch_col<BLOCK>(0), ACC = scratch_col<BLOCK>(13), T = scratch_col<BLOCK>(26), INV = scratch_col<BLOCK>(56);
+__device__ __noinline__ void ode_fwd_stage_call(int tid, int lane0, double ul, double ur, int s, double* rec, double* act) {
+    const Scratch<BLOCK> X{g_smem + tid}, ACC{g_smem + 13 * BLOCK + tid}, T{g_smem + 26 * BLOCK + tid}, INV{g_smem + 56 * BLOCK + tid};
     double x[13], k[13];
 #pragma unroll
     for (int c = 0; c < 13; c++) x[c] = T[c];
@@ -131,9 +133,10 @@ template <int TERR, int BLOCK, bool STORE> struct FusedStep {
         const size_t act_stride = act_stage_doubles(NK);
         double* act = STORE ? a.act + (step * 4) * act_stride + act_lane_offset((size_t)blockIdx.x * BLOCK + threadIdx.x) : nullptr;
         const size_t rec_stride = NK * kCkRows;
+        const int tid = (int)threadIdx.x;
 #pragma unroll 1
         for (int s = 0; s < 4; s++)
-            ode_fwd_stage_call<TERR, BLOCK, STORE>(lane0, ul, ur, s, rec ? rec + (size_t)s * rec_stride : nullptr, STORE ? act + (size_t)s * act_stride : nullptr);
+            ode_fwd_stage_call<TERR, BLOCK, STORE>(tid, lane0, ul, ur, s, rec ? rec + (size_t)s * rec_stride : nullptr, STORE ? act + (size_t)s * act_stride : nullptr);
         inv_carry = scratch_col<BLOCK>(56)[0];
     }
 };

@@ -391,6 +391,8 @@ struct NNAct {
 
 // in: contact velocity (vx, vy), wheel speed w, sinkage zr -> (Fx, Fy, Fz) before the damping term.
 // Loop nests are ordered so that consecutive instructions belong to different accumulators (ILP).
+// in: contact velocity (vx, vy), wheel speed w, sinkage zr -> (Fx, Fy, Fz) before the damping term.
+// Loop nests are ordered so that consecutive instructions belong to different accumulators (ILP).
 template <bool WANT_D = false>
 AVS_HD void tire_nn_fwd(const ModelConst& mc, double vx, double vy, double w, double zr, double F[3], NNAct& a) {
     const double s0 = zr * (1.0 / kInStd0);
