@@ -14,8 +14,9 @@ blocks, each with its own kernel time, clocks and roofline: `configs1_forward_on
 (Bekker on height / soil grids, 8192 per GPU x 600) and `strong_scaling` (configs[4]: 65536 windows per step split over the ranks).
 `roofline` comes from hardware counters: FP64 instruction counts per vehicle-step of the committed ncu capture of THIS build
 (profiles/r2_counters.json, tied by a hash of the kernel sources) over kernel durations measured live.
-The reference arm times the reference algorithm's CPU restatement (oracle/, the reference itself cannot be
-built here: CppAD / iit-rbd / Eigen absent) on the box's host cores.
+The reference arm (and `cpu_baseline`) time the reference's OWN Trainer::trainTrajectory on the box's host cores: oracle/_ref is
+built from the reference's first-party sources in place, behind stand-in headers for its absent third-party libraries (Eigen,
+CppAD, iit-rbd: oracle/refshim/); without that prebuilt library they fall back to the oracle restatement (kind "port").
 """
 import argparse
 import json
@@ -153,10 +154,46 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_baseline_fwd_adj(T, threads, n_traj, repeats=1):
-    """Oracle (reference restatement) fwd + reverse-tape gradient on `threads` host threads."""
+def _windows_for_reference(n_traj, T, seed):
+    """synthetic batch -> GroundTruthDataRow windows [n][T][10] (time, vl, vr, x, y, z, yaw, wz, vx, vy) as Trainer::loadDataFile
+    yields them; Trainer's initializeState on row 0 reproduces synth.make_batch's x0 exactly"""
     import numpy as np
     from auvsl_neural_ode_b200 import synth
+    x0, ctrl, gt = synth.make_batch(n_traj, T, seed=seed)
+    vl = np.concatenate([ctrl[:, 0, :], ctrl[-1:, 0, :]])
+    vr = np.concatenate([ctrl[:, 1, :], ctrl[-1:, 1, :]])
+    rows = np.zeros((n_traj, T, 10))
+    for n in range(n_traj):
+        v = synth.B @ np.stack([vl[:, n], vr[:, n]])
+        rows[n, :, 0] = np.arange(T) * 0.01
+        rows[n, :, 1], rows[n, :, 2] = vl[:, n], vr[:, n]
+        rows[n, :, 3], rows[n, :, 4], rows[n, :, 5], rows[n, :, 6] = gt[:, 1, n], gt[:, 2, n], synth.Z_STABLE_NN, gt[:, 0, n]
+        rows[n, :, 7], rows[n, :, 8], rows[n, :, 9] = v[2], v[0], v[1]
+    return rows
+
+
+def cpu_baseline_fwd_adj(T, threads, n_traj, repeats=1):
+    """The reference's CPU path on `threads` host threads, one trajectory per thread like Trainer::Worker.
+    kind "reference": oracle/_ref — the reference's OWN Trainer::trainTrajectory (CppAD-style tape + Reverse(1)), compiled in
+    place from its sources behind the stand-in Eigen / CppAD / iit-rbd headers of oracle/refshim/;
+    kind "port": the oracle restatement, when the prebuilt reference library is not there.
+    Returns (vehicle-steps/s, seconds, kind)."""
+    import numpy as np
+    from auvsl_neural_ode_b200 import synth
+    from oracle import pyref
+    if pyref.available():
+        from concurrent.futures import ThreadPoolExecutor
+        rows = _windows_for_reference(n_traj, T, synth.SEED + 17)
+        P = pyref.default_params(0)
+        pyref.train_trajectory(P, 0, rows[0][:3])  # load + first-call costs outside the timed region
+        best = None
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            with ThreadPoolExecutor(max_workers=threads) as ex:  # ctypes releases the GIL; the tape is thread_local
+                list(ex.map(lambda w: pyref.train_trajectory(P, 0, w)[0], rows))
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        return n_traj * (T - 1) * 10 / best, best, "reference"
     from oracle import pyoracle as po
     x0, ctrl, gt = synth.make_batch(n_traj, T, seed=synth.SEED + 17)
     p = po.nn_default_params()
@@ -167,22 +204,30 @@ def cpu_baseline_fwd_adj(T, threads, n_traj, repeats=1):
         po.rollout_grad_batch(p, flat, x0, ctrl, gt, T, nthreads=threads, per_sample=False)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
-    return n_traj * (T - 1) * 10 / best, best
+    return n_traj * (T - 1) * 10 / best, best, "port"
+
+
+CPU_KIND_NOTE = {
+    "reference": "the reference's own first-party sources (Trainer::trainTrajectory -> VehicleSystem::integrate -> HybridDynamics::RK4/ODE -> "
+                 "TireNetwork / generated ForwardDynamics), compiled in place (-O2) against stand-in headers for its absent third-party libraries "
+                 "(Eigen, CppAD, iit-rbd: oracle/refshim/); its CMake build cannot run here",
+    "port": "oracle restatement (the prebuilt oracle/_ref library is absent); flatters the CPU: plain double forward + a minimal tape",
+}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import pyoracle as po
-    cores = po.hardware_threads() or os.cpu_count() or 1
+    cores = os.cpu_count() or 1
     T = args.rows
-    n_traj = 8 * cores  # a bounded sample per step (a few seconds), so the whole run ends within minutes
-    for _ in range(max(args.warmup, 0) and 1):  # one short warm-up pass is enough for a CPU code path
+    n_traj = 2 * cores  # a bounded sample per step (a few seconds), so the whole run ends within minutes
+    if args.warmup > 0:  # one short warm-up pass is enough for a CPU code path
         cpu_baseline_fwd_adj(min(T, 20), cores, cores)
     t0 = time.perf_counter()
+    kind = "port"
     for _ in range(args.steps):
-        cpu_baseline_fwd_adj(T, cores, n_traj)
+        _, _, kind = cpu_baseline_fwd_adj(T, cores, n_traj)
     dt = time.perf_counter() - t0
     units = args.steps * n_traj * (T - 1) * 10
     value = units / dt
@@ -193,11 +238,10 @@ def run_reference(args):
         "data": "synthetic",
         "config": {"workload": f"configs[2] sample: NN tire model + adjoint, T={T}, {n_traj} trajectories/step on host CPU", "rows": T,
                    "substeps": 10, "terrain": "flat"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "reference cannot be built here (CppAD, iit-rbd, Eigen3 absent); this is the oracle restatement, which flatters the CPU "
-                "(plain double forward + minimal tape instead of CppAD::AD<double>)",
+        "note": CPU_KIND_NOTE[kind],
     }
     print(json.dumps(out))
 
@@ -397,16 +441,15 @@ def run_b200(args):
         roofline["kernel_share_of_step"] = {"rollout_fwd_kernel<NN,flat,STORE>": f_ms / (ms_max / args.steps), "rollout_bwd2_kernel<flat>": b_ms / (ms_max / args.steps)}
         cpu = None
         if not args.no_cpu_baseline:
-            from oracle import pyoracle as po
-            cores = po.hardware_threads() or os.cpu_count() or 1
-            n_traj = 32 * cores  # ~10 s of CPU work on all host threads
-            v_all, dt_all = cpu_baseline_fwd_adj(T, cores, n_traj)
-            v_one, dt_one = cpu_baseline_fwd_adj(T, 1, 2)
+            cores = os.cpu_count() or 1
+            n_traj = 8 * cores  # ~10-20 s of CPU work on all host threads
+            v_all, dt_all, kind = cpu_baseline_fwd_adj(T, cores, n_traj)
+            v_one, dt_one, _ = cpu_baseline_fwd_adj(T, 1, 2)
             ops = cpu_reference_op_counts()
-            cpu = {"value": v_all, "unit": UNIT, "cores": cores, "kind": "port",
+            cpu = {"value": v_all, "unit": UNIT, "cores": cores, "kind": kind,
                    "sample": f"{n_traj} trajectories x {T} rows, fwd + reverse-tape gradient, {cores} threads ({dt_all:.1f} s); "
                              f"single thread: {v_one:.1f} {UNIT} on 2 trajectories ({dt_one:.1f} s)",
-                   "single_thread_value": v_one, "reference_formulation_ops": ops}
+                   "single_thread_value": v_one, "what": CPU_KIND_NOTE[kind], "reference_formulation_ops": ops}
             # secondary, clearly named: useful work measured in the REFERENCE formulation's operations (what CppAD would execute per
             # RK4 step: dense 6x6 products, LLT every call, the z-network's 256 tanh ...), not what the kernels execute
             fe = ops["nn_flop_equiv"]

@@ -21,6 +21,11 @@ def golden():
     return np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_v1.npz"))
 
 
+def golden_ref():
+    """inputs / outputs of the reference's OWN code (tests/golden/make_golden_ref.py, oracle/ref_capi.cpp)"""
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_ref_v1.npz"))
+
+
 def rel_state_err(a, b):
     """1e-9 'relative' for states: relative to max(1, |value|) (angles / positions near 0 are absolute)."""
     return float(np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b))))
@@ -64,6 +69,60 @@ def bk():
     c = capi.Context(0, capi.TIRE_BEKKER)
     yield c
     c.close()
+
+
+def test_cuda_path_vs_reference_own_numbers(nn, bk):
+    """The CUDA path against numbers produced by THE REFERENCE'S OWN CODE (first-party sources compiled in place behind stand-in
+    third-party headers; fixture generated in the build container, where /root/reference exists): ODE values, every row of
+    120-row rollouts on flat and bumpy terrain, final states after 600 rows, Trainer::trainTrajectory losses and gradients at
+    T = 20 and T = 200, the RMSProp update, settle; Bekker ODE values and 100-row rollouts.  Bars: 1e-9 / 1e-7."""
+    R = golden_ref()
+    P_, PB_ = R["nn_params"], R["bekker_params"]
+    assert np.array_equal(P_, capi.nn_default_params()) and np.array_equal(PB_, capi.bekker_default_params())
+    nn.set_nn_params(P_)
+    bk.set_bekker_params(PB_)
+    report = {}
+    for ctx, tire in ((nn, 0), (bk, 1)):
+        worst = 0.0
+        for terr in (capi.FLAT, capi.SLOPE, capi.BUMPY):
+            ctx.set_terrain(terr)
+            X, U, Xd = R[f"ode_{tire}_{terr}_X"], R[f"ode_{tire}_{terr}_U"], R[f"ode_{tire}_{terr}_Xd"]
+            worst = max(worst, rel_state_err(ctx.ode(X.T.copy(), U.T.copy()).T, Xd))
+        report[f"ode tire {tire}"] = worst
+        assert worst < STATE_RTOL
+    nn.set_terrain(capi.FLAT)
+    report["settle nn"] = rel_state_err(nn.settle()[[0, 1, 2, 3, 6]], R["settle_nn"][[0, 1, 2, 3, 6]])
+    bk.set_terrain(capi.FLAT)
+    report["settle bekker"] = rel_state_err(bk.settle()[[0, 1, 2, 3, 6]], R["settle_bekker"][[0, 1, 2, 3, 6]])
+    for tag, ctx, terr, T in (("roll_nn_flat", nn, capi.FLAT, 120), ("roll_nn_bumpy", nn, capi.BUMPY, 120), ("roll_bekker_flat", bk, capi.FLAT, 100)):
+        ctx.set_terrain(terr)
+        xl, _ = ctx.rollout(R[tag + "_x0"], R[tag + "_ctrl"], T)
+        report[tag] = rel_state_err(xl, R[tag + "_xlist"])
+    nn.set_terrain(capi.FLAT)
+    _, xf = nn.rollout(R["roll_nn_flat600_x0"], R["roll_nn_flat600_ctrl"], 600, want_list=False)
+    report["roll_nn_flat600 final"] = rel_state_err(xf, R["roll_nn_flat600_xfinal"])
+    for k, v in report.items():
+        assert v < STATE_RTOL, (k, v)
+    for tag, terr, T in (("grad_flat20", capi.FLAT, 20), ("grad_slope20", capi.SLOPE, 20), ("grad_bumpy20", capi.BUMPY, 20), ("grad_flat200", capi.FLAT, 200)):
+        nn.set_terrain(terr)
+        nn.set_nn_params(R[tag + "_params"])
+        loss, red, gps = nn.rollout_grad(R[tag + "_x0"], R[tag + "_ctrl"], R[tag + "_gt"], T)
+        np.testing.assert_allclose(loss, R[tag + "_loss"], rtol=1e-9)
+        g = R[tag + "_grad"]
+        e = float(np.max(np.abs(gps - g) / np.abs(g).max(axis=0)))
+        report[tag + " grad"] = e
+        assert e < GRAD_RTOL, (tag, e)
+        assert np.all(gps[104:] == 0.0)
+    nn.set_terrain(capi.FLAT)
+    nn.set_nn_params(P_)
+    nn.reset_optimizer()
+    red = np.zeros(418)
+    red[:416], red[417] = R["rmsprop_grad"] * 4, 4
+    nn.rmsprop_step(red)
+    np.testing.assert_allclose(nn.get_nn_params(), R["rmsprop_params"], rtol=1e-14, atol=0)
+    nn.set_nn_params(P)
+    nn.reset_optimizer()
+    print("[reference parity] CUDA path vs the reference's own numbers: " + ", ".join(f"{k} {v:.2e}" for k, v in report.items()))
 
 
 def test_ode_vs_golden(nn):
