@@ -85,7 +85,10 @@ def roofline_block(counters, kernel, units, kernel_ms, fp64_peak_tflops, hbm_pea
         "achieved_definition": "FP64 thread-instructions/s x 2 flop (issue slots of the FP64 pipe)",
         "executed_flops_tflops": flops / sec / 1e12, "executed_flops_frac": flops / sec / 1e12 / fp64_peak_tflops,
         "fp64_thread_inst_per_vehicle_step": {"dfma": per["dfma"], "dmul": per["dmul"], "dadd": per["dadd"]},
-        "ncu_pipe_fp64_active_pct_at_capture": k.get("pipe_fp64_active_pct"),
+        # ncu's own reading of the same pipe at capture time: share of ELAPSED cycles over all SMs (comparable with frac, which is
+        # relative to the measured DFMA peak = 94 % of the datasheet rate) and share of cycles of the SMs that were active
+        "ncu_pipe_fp64_pct_of_elapsed_at_capture": k.get("pipe_fp64_elapsed_pct"),
+        "ncu_pipe_fp64_pct_of_active_at_capture": k.get("pipe_fp64_active_pct"),
         "traffic": traffic, "traffic_unit": "B per launch (dram__bytes_read + dram__bytes_write, ncu)",
         "traffic_over_algorithmic": (per["dram_read_bytes"] + per["dram_write_bytes"]) / ALGORITHMIC_HBM_B_PER_STEP,
         "hbm_gbs": traffic / sec / 1e9, "hbm_frac_of_measured_peak": traffic / sec / 1e9 / hbm_peak_gbs if hbm_peak_gbs else None,
@@ -453,11 +456,14 @@ def run_b200(args):
             # secondary, clearly named: useful work measured in the REFERENCE formulation's operations (what CppAD would execute per
             # RK4 step: dense 6x6 products, LLT every call, the z-network's 256 tanh ...), not what the kernels execute
             fe = ops["nn_flop_equiv"]
-            roofline["algorithmic_vs_reference_formulation"] = {
+            roofline["reference_formulation_work"] = {
                 "flop_equiv_per_vehicle_step_forward": fe,
-                "definition": "oracle count_ops of one RK4 step (dense reference formulation) with SURVEY 8(d) weights; fwd+adjoint taken as 3 x forward (tape forward + reverse sweep)",
-                "whole_step_frac": 3.0 * fe * value / world / 1e12 / fp64_peak,
-                "forward_only_frac": (fe * extra["configs1_forward_only"]["value"] / world / 1e12 / fp64_peak) if "configs1_forward_only" in extra else None}
+                "definition": "NOT a roofline fraction: the rate at which the run retires the REFERENCE formulation's operations (oracle count_ops of "
+                              "one RK4 step: dense 6x6 products, LLT per call, 512 tanh ... with SURVEY 8(d) weights; fwd+adjoint taken as 3 x forward), "
+                              "in TFLOP/s-equivalents.  It exceeds the FP64 peak because the kernels fold most of that work away (DESIGN.md section 2)",
+                "whole_step_equiv_tflops": 3.0 * fe * value / world / 1e12,
+                "forward_only_equiv_tflops": (fe * extra["configs1_forward_only"]["value"] / world / 1e12) if "configs1_forward_only" in extra else None,
+                "fp64_peak_tflops": fp64_peak}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",

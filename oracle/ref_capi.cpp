@@ -10,6 +10,7 @@
 // semantics are stated in their headers.  So: first-party arithmetic = the reference's own code; third-party arithmetic =
 // restated from the published definitions (rounding-level differences only are possible there).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <iostream>
 #include <memory>
@@ -43,13 +44,18 @@ std::shared_ptr<System<ADF>> mkSystem(int tire, int terr, const double* params) 
     sys->setParams(p);
     return sys;
 }
-// the reference prints progress lines to std::cout; keep the host process' stdout clean
-struct Quiet {
-    std::streambuf* old;
-    std::ostringstream sink;
-    Quiet() : old(std::cout.rdbuf(sink.rdbuf())) {}
-    ~Quiet() { std::cout.rdbuf(old); }
+// The reference prints progress lines to std::cout.  libstdc++ is linked statically into this library, so its std::cout is
+// private to it: it is pointed at a sink ONCE, for good (swapping the buffer per call would race between the host's threads
+// and leave a dangling buffer behind for the flush at exit).  The sink is leaked on purpose.
+struct NullBuf : std::streambuf {
+    int overflow(int c) override { return c; }
+    std::streamsize xsputn(const char*, std::streamsize n) override { return n; }
 };
+struct QuietOnce {
+    QuietOnce() { if (!std::getenv("JACKAL_REF_VERBOSE")) std::cout.rdbuf(new NullBuf()); }
+};
+QuietOnce g_quiet_once;
+struct Quiet {};  // (marks the entry points whose callees print)
 GroundTruthDataRow mkRow(const double* r) {  // (time, vl, vr, x, y, z, yaw, wz, vx, vy), as oracle_capi.cpp
     GroundTruthDataRow g;
     g.time = r[0]; g.vl = r[1]; g.vr = r[2]; g.x = r[3]; g.y = r[4]; g.z = r[5]; g.yaw = r[6]; g.wz = r[7]; g.vx = r[8]; g.vy = r[9];

@@ -32,7 +32,8 @@ struct Tape {
     std::size_t hint = 0;  // size of the thread's previous recording: reserved up front by the next Independent()
     int push(int a, double da, int b, double db) { nodes.push_back(Node{a, b, da, db}); return (int)nodes.size() - 1; }
 };
-inline Tape& tape() { static thread_local Tape t; return t; }
+// one tape per thread, heap-allocated and never destroyed: no thread-exit destructor runs inside a dlopen'ed library
+inline Tape& tape() { static thread_local Tape* t = nullptr; if (!t) t = new Tape(); return *t; }
 }  // namespace shim
 
 template <class Base> class AD;

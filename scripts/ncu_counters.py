@@ -54,6 +54,8 @@ for r in data:
         "duration_ms": val(r, "gpu__time_duration.sum", True), "grid": val(r, "launch__grid_size"), "block": val(r, "launch__block_size"),
         "registers": val(r, "launch__registers_per_thread"), "dyn_smem_bytes": val(r, "launch__shared_mem_per_block_dynamic", True),
         "pipe_fp64_active_pct": val(r, "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+        # the same counter over ELAPSED cycles of all SMs (idle SMs of a grid smaller than the chip count): the whole-chip figure
+        "pipe_fp64_elapsed_pct": val(r, "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed"),
         "issue_active_pct": val(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
         "warps_active_pct": val(r, "sm__warps_active.avg.pct_of_peak_sustained_active"),
         "warp_inst_executed": val(r, "smsp__inst_executed.sum"), "warp_inst_pipe_fp64": val(r, "sm__inst_executed_pipe_fp64.sum"),
