@@ -308,7 +308,9 @@ def run_b200(args):
     trainer = BatchTrainer(ctx, dev, explode_mode=capi.EXPLODE_DROP_SAMPLE)
     trainer.init_native_comm()  # world > 1: the all-reduce is avs_allreduce_dev (ncclAllReduce on the context's stream, C ABI)
     if stdout_saved is not None:
+        import ctypes
         sys.stdout.flush()
+        ctypes.CDLL(None).fflush(None)  # NCCL writes its banner through C stdio: push it out while fd 1 still points at stderr
         os.dup2(stdout_saved, 1)
         os.close(stdout_saved)
     steps_per_call = N * (T - 1) * sub

@@ -60,10 +60,10 @@ if rank == 0:
     w_, r_, ver = ctx.comm_info()
     ssum, wsum = 0.0, 0.0
     for i in range(416):  # same accumulation order as synth_demo.cpp
-        ssum += p[i]
-        wsum += float(i + 1) * p[i]
+        ssum += float(p[i])
+        wsum += float(i + 1) * float(p[i])
     print(f"dp_train_csv: world={world} native_comm={tr.native_comm} nccl={ver} windows={N} n_kept={int(red[417].item())} ranks_bit_identical={same}")
-    print(f"params sum {ssum!r} weighted {wsum!r} p[0] {p[0]!r} p[103] {p[103]!r}")
+    print(f"params sum {ssum!r} weighted {wsum!r} p[0] {float(p[0])!r} p[103] {float(p[103])!r}")
     assert same
 dist.barrier()
 ctx.comm_destroy()
