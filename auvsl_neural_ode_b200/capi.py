@@ -25,7 +25,7 @@ EXPORTS = [
     "avs_rollout", "avs_rollout_dev", "avs_rollout_grad", "avs_rollout_grad_dev", "avs_rmsprop_step_dev", "avs_rmsprop_step", "avs_reset_optimizer",
     "avs_stream", "avs_set_stream", "avs_use_own_stream", "avs_sync", "avs_kernel_launches", "avs_last_kernel_ms", "avs_measure_fp64_peak",
     "avs_rollout_margins", "avs_comm_unique_id", "avs_comm_init_rank", "avs_comm_init_all", "avs_comm_destroy", "avs_comm_info",
-    "avs_allreduce_dev", "avs_allreduce", "avs_alloc_pinned", "avs_free_pinned", "avs_set_reduced",
+    "avs_allreduce_dev", "avs_allreduce", "avs_alloc_pinned", "avs_free_pinned", "avs_set_reduced", "avs_set_contact_search", "avs_load_legacy_net_csv", "avs_mlp_forward",
 ]
 NUM_MARGINS = 6
 MARGIN_KINDS = ("contact |sinkage|", "Fx sign |wR - vx|", "slip clamps", "|pgc - pg| / pg", "|R - sinkage|", "arc |dtheta|")
@@ -88,6 +88,9 @@ def lib():
         L.avs_alloc_pinned.argtypes = [C.POINTER(vp), C.c_ulonglong]
         L.avs_free_pinned.argtypes = [vp]
         L.avs_set_reduced.argtypes = [vp, vp]
+        L.avs_set_contact_search.argtypes = [vp, i32]
+        L.avs_load_legacy_net_csv.argtypes = [C.c_char_p, vp]
+        L.avs_mlp_forward.argtypes = [vp, i32, vp, i32, vp, vp]
         _lib = L
     return _lib
 
@@ -123,6 +126,18 @@ def init_state_com(start21):
     out = np.zeros(21)
     lib().avs_init_state_com(_p(s), _p(out))
     return out
+
+
+MLP_BASE_NETWORK, MLP_LEGACY_TIRE = 0, 1
+
+
+def load_legacy_net_csv(path):
+    """data/nn_pretrained.csv -> the 435 numbers W0 (16x5), b0, W2 (16x16), b2, W4 (3x16), b4, out_mean, out_std, in_mean, in_std"""
+    p = np.zeros(435)
+    rc = lib().avs_load_legacy_net_csv(os.fsencode(path), _p(p))
+    if rc != 0:
+        raise AvsError(f"avs_load_legacy_net_csv({path}): {lib().avs_strerror(rc).decode()} (need exactly 435 numbers)")
+    return p
 
 
 def comm_unique_id():
@@ -200,6 +215,18 @@ class Context:
             s = _f64(soil)
             assert s.shape == (5, ny, nx)
         self._ck(lib().avs_set_terrain_grid(self._h, _p(h), _p(s), nx, ny, x0, y0, dx, dy))
+
+    def set_contact_search(self, on):
+        """10-angle contact search (HybridDynamics::get_tire_cpts_sinkages_fancy) instead of the point under the hub; forward only."""
+        self._ck(lib().avs_set_contact_search(self._h, 1 if on else 0))
+
+    def mlp_forward(self, kind, params, x):
+        """BaseNetwork::forward (kind 0, params[131], x [3][N]) or the nn_pretrained.csv network (kind 1, params[435], x [5][N]) -> [3][N]"""
+        params, x = _f64(params), _f64(x)
+        N = x.shape[1]
+        out = np.zeros((3, N))
+        self._ck(lib().avs_mlp_forward(self._h, int(kind), _p(params), N, _p(x), _p(out)))
+        return out
 
     def set_checkpoint_budget(self, nbytes):
         self._ck(lib().avs_set_checkpoint_budget(self._h, int(nbytes)))

@@ -4,6 +4,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -231,6 +232,7 @@ int avs_create(avs_ctx** out, int device, int tire_model) {
     memcpy(ctx->mc.Z4, kFixedZ4, sizeof(kFixedZ4));
     memcpy(ctx->mc.bek, kBekkerDefault, sizeof(kBekkerDefault));
     compute_AIinv(ctx->mc.AIinv);
+    fill_contact_search(ctx->mc);
     ctx->mc.grid.inv_dx = ctx->mc.grid.inv_dy = 1.0;
     bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
     ctx->stream = ctx->own_stream;
@@ -326,6 +328,12 @@ int avs_set_terrain_grid(avs_ctx* ctx, const double* height, const double* soil,
     ctx->mc.grid.inv_dx = 1.0 / dx; ctx->mc.grid.inv_dy = 1.0 / dy;
     ctx->terr = AVS_TERRAIN_GRID;
     ctx->mc.terr_kind = AVS_TERRAIN_GRID;
+    return AVS_OK;
+}
+
+int avs_set_contact_search(avs_ctx* ctx, int on) {
+    if (!ctx || (on != 0 && on != 1)) return fail(ctx, AVS_E_ARG, "avs_set_contact_search: on must be 0 or 1");
+    ctx->mc.contact_search = on;
     return AVS_OK;
 }
 
@@ -440,6 +448,7 @@ static int rollout_grad_impl(avs_ctx* ctx, int N, int T, int substeps, const dou
     if (!ctx || N <= 0 || T < 2 || substeps < 1 || !d_x0 || !d_ctrl || !d_gt || (explode_mode != 0 && explode_mode != 1))
         return fail(ctx, AVS_E_ARG, "avs_rollout_grad: bad argument (N=%d T=%d substeps=%d mode=%d)", N, T, substeps, explode_mode);
     if (ctx->tire != AVS_TIRE_NN) return fail(ctx, AVS_E_STATE, "avs_rollout_grad: the adjoint exists for the NN tire model only");
+    if (ctx->mc.contact_search) return fail(ctx, AVS_E_STATE, "avs_rollout_grad: the 10-angle contact search is forward only (the reference never tapes it)");
     CK(cudaSetDevice(ctx->device));
     const size_t n = (size_t)N;
     if (!d_loss) { CK(ctx->loss.reserve(n * 8)); d_loss = ctx->loss.as<double>(); }
@@ -561,6 +570,40 @@ int avs_rmsprop_step(avs_ctx* ctx, const double* reduced_host, double lr, double
     int rc = avs_set_reduced(ctx, reduced_host);
     if (rc) return rc;
     return avs_rmsprop_step_dev(ctx, ctx->reduced.as<double>(), lr, l1_weight);
+}
+
+// ---- the reference's auxiliary networks as batched device functions ------------------------------------------------------
+int avs_load_legacy_net_csv(const char* path, double* params435) {
+    if (!path || !params435) return AVS_E_ARG;
+    FILE* f = fopen(path, "r");
+    if (!f) return AVS_E_ARG;
+    // one number per line; line 426 of the reference's file carries a junk token after the number ("285.06...;in_mean 0.0",
+    // i.e. two numbers): every token that parses as a number counts, anything else is skipped
+    int n = 0;
+    char tok[256];
+    while (n < kLegacyNetParams + 1 && fscanf(f, " %255[^ \t\r\n;,]", tok) == 1) {
+        char* end = nullptr;
+        const double v = strtod(tok, &end);
+        if (end != tok && *end == '\0') { if (n < kLegacyNetParams) params435[n] = v; n++; }
+        int c = fgetc(f);  // the delimiter
+        (void)c;
+    }
+    fclose(f);
+    return n == kLegacyNetParams ? AVS_OK : AVS_E_ARG;
+}
+int avs_mlp_forward(avs_ctx* ctx, int kind, const double* params, int N, const double* in, double* out) {
+    if (!ctx || !params || N <= 0 || !in || !out || (kind != MLP_BASE_NETWORK && kind != MLP_LEGACY_TIRE)) return fail(ctx, AVS_E_ARG, "avs_mlp_forward: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    const int np = kind == MLP_BASE_NETWORK ? kBaseNetParams : kLegacyNetParams, nin = kind == MLP_BASE_NETWORK ? 3 : 5;
+    const size_t n = (size_t)N;
+    CK(ctx->io_a.reserve(nin * n * 8)); CK(ctx->io_b.reserve(np * 8)); CK(ctx->io_c.reserve(3 * n * 8));
+    CK(cudaMemcpyAsync(ctx->io_a.p, in, nin * n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->io_b.p, params, np * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(launch_mlp(kind, ctx->io_b.as<double>(), N, ctx->io_a.as<double>(), ctx->io_c.as<double>(), ctx->stream));
+    ctx->launches++;
+    CK(cudaMemcpyAsync(out, ctx->io_c.p, 3 * n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return AVS_OK;
 }
 
 // ---- pinned host staging ----------------------------------------------------------------------------------------------

@@ -23,11 +23,16 @@ cudaError_t launch_settle(int tire, const ModelConst& mc, const double* d_live, 
 cudaError_t launch_filter_reduce(const double* gps, const double* loss, int N, double thresh, int mode, unsigned char* flags, double* reduced, cudaStream_t s);
 // RMSProp (Trainer::updateParams)
 cudaError_t launch_rmsprop(double* params416, double* sq416, const double* reduced418, double lr, double l1, cudaStream_t s);
+// the reference's auxiliary networks as batched functions (avs_k_mlp.cu): in [n_in][N] -> out [3][N]
+enum { MLP_BASE_NETWORK = 0, MLP_LEGACY_TIRE = 1 };
+constexpr int kBaseNetParams = 131, kLegacyNetParams = 435;
+cudaError_t launch_mlp(int kind, const double* d_params, int N, const double* d_in, double* d_out, cudaStream_t s);
 // DFMA-chain peak probe
 cudaError_t launch_fp64_peak(int blocks, int threads, int iters, double* sink, cudaStream_t s);
 
 inline cudaError_t launch_rollout_fwd(int tire, int terr, bool store, const ModelConst& mc, const double* d_live, const RolloutArgs& a, cudaStream_t s) {
-    if (tire == TIRE_NN) return terr == TERR_FLAT ? launch_fwd_nn_flat(store, mc, d_live, a, s) : launch_fwd_nn_dyn(store, mc, d_live, a, s);
+    // the flat-terrain instantiation is the lean one (no terrain switch, no contact search): everything else runs on TERR_DYN
+    if (tire == TIRE_NN) return (terr == TERR_FLAT && !mc.contact_search) ? launch_fwd_nn_flat(store, mc, d_live, a, s) : launch_fwd_nn_dyn(store, mc, d_live, a, s);
     if (store) return cudaErrorInvalidValue;
     return launch_fwd_bekker(mc, a, s);
 }

@@ -87,7 +87,20 @@ struct ModelConst {
     GridTerrain grid;
     const double* ztab;                   // [kZTabN][kZTabDeg+1] piecewise polynomial of the fixed z-net (build_ztab)
     int terr_kind;                        // used by the TERR_DYN instantiations
+    // optional 10-angle contact search (HybridDynamics::get_tire_cpts_sinkages_fancy, HybridDynamics.cpp:258-316), TERR_DYN
+    // instantiations only: sin / cos of the candidate pitch angles -0.3 ... +0.3 rad (filled by fill_contact_search)
+    int contact_search;
+    double cs_sin[10], cs_cos[10];
 };
+inline void fill_contact_search(ModelConst& mc) {
+    const double max_angle = -.3;
+    const int max_checks = 10;
+    for (int jj = 0; jj < max_checks; jj++) {
+        const double a = max_angle - (2 * max_angle * jj / ((double)max_checks - 1));  // :293
+        mc.cs_sin[jj] = sin(a);
+        mc.cs_cos[jj] = cos(a);
+    }
+}
 
 // ------------------------------------------------------------------------------------------------
 // fp64 tanh.  tanh|x| = (1-e)/(1+e), e = exp(-2|x|): one exp (Cody-Waite reduction + degree-11
@@ -632,16 +645,44 @@ struct WheelAct {
 
 struct NullAcc { AVS_HD void record(const double*) {} };
 
+// Contact search of HybridDynamics::get_tire_cpts_sinkages_fancy (HybridDynamics.cpp:258-316; roty utils.cpp:5-17): ten
+// candidate points on the rim, test_pos = joint + R roty(a) (0, 0, -r) = joint - r (R[:,0] sin a + R[:,2] cos a); the sinkage
+// is the largest candidate sinkage (0 when none is positive: max_sinkage starts at 0), the reported point the JOINT centre.
+// Forward only (the reference never tapes this function); dax / day are the terrain gradient at the selected candidate.
+template <int TERR>
+AVS_HD void wheel_contact_search(const ModelConst& mc, double tx, double ty, const double R[9], const double X[13], double& sink, double& dax, double& day, double cp[3]) {
+    const double* p = X + 4;
+#pragma unroll
+    for (int i = 0; i < 3; i++) cp[i] = (R[3 * i] * tx + R[3 * i + 1] * ty + R[3 * i + 2] * kTz) + p[i];
+    double best = 0.0;
+    dax = 0.0; day = 0.0;
+#pragma unroll 1
+    for (int jj = 0; jj < 10; jj++) {
+        const double sa = mc.cs_sin[jj], ca = mc.cs_cos[jj];
+        double tp[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) tp[i] = cp[i] + (R[3 * i] * sa + R[3 * i + 2] * ca) * (-kTireRadius);
+        double gx, gy;
+        const double sk = altitude<TERR>(mc, tp[0], tp[1], gx, gy) - tp[2];
+        if (sk > best) { best = sk; dax = gx; day = gy; }
+    }
+    sink = best;
+}
+
 // wheel index i: 0 FL(+,+) 1 FR(+,-) 2 RL(-,+) 3 RR(-,-); qd = commanded wheel speed
 template <int TERR>
 AVS_HD void wheel_contact(const ModelConst& mc, double tx, double ty, const double R[9], const double X[13], double& sink, double cv[3],
                           double& dax, double& day, double cp[3]) {
     const double* p = X + 4; const double* w = X + 7; const double* v = X + 10;
-    cp[0] = fma(R[0], tx, fma(R[1], ty, fma(R[2], kRz, p[0])));
-    cp[1] = fma(R[3], tx, fma(R[4], ty, fma(R[5], kRz, p[1])));
-    cp[2] = fma(R[6], tx, fma(R[7], ty, fma(R[8], kRz, p[2])));
-    const double alt = altitude<TERR>(mc, cp[0], cp[1], dax, day);
-    sink = alt - cp[2];
+    if (TERR == TERR_DYN && mc.contact_search) {
+        wheel_contact_search<TERR>(mc, tx, ty, R, X, sink, dax, day, cp);
+    } else {
+        cp[0] = fma(R[0], tx, fma(R[1], ty, fma(R[2], kRz, p[0])));
+        cp[1] = fma(R[3], tx, fma(R[4], ty, fma(R[5], kRz, p[1])));
+        cp[2] = fma(R[6], tx, fma(R[7], ty, fma(R[8], kRz, p[2])));
+        const double alt = altitude<TERR>(mc, cp[0], cp[1], dax, day);
+        sink = alt - cp[2];
+    }
     // cv = v - r^ w = v + w x r       (HybridDynamics.cpp:336-346)
     cv[0] = v[0] + (w[1] * kRz - w[2] * ty);
     cv[1] = v[1] + (w[2] * tx - w[0] * kRz);

@@ -1,10 +1,16 @@
 // BaseNetwork.h — API surface of the reference's base-link residual network (reference src/BaseNetwork.{h,cpp}).
 // In the reference this 3-8-8-3 MLP with biases (131 parameters) is dead code: its forward call is commented out
 // (src/auvsl_dynamics/HybridDynamics.cpp:433) and get_base_f_ext is never invoked (:557).  It is therefore NOT on
-// the GPU path; this host-only class keeps the type, parameter packing and forward semantics available.
+// the rollout kernels; this class keeps the type, parameter packing and forward semantics available on the host, and
+// forwardBatch() evaluates the same function for N inputs at once on the GPU through the C ABI (avs_mlp_forward).
+// LegacyTireNet below is the loader + batched evaluation of the orphan data/nn_pretrained.csv network.
 #pragma once
 #include <cmath>
 #include <cstdlib>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "../../include/avsim.h"
 #include "types/VecX.h"
 
 class BaseNetwork {
@@ -50,6 +56,15 @@ public:
     void setParams(const VectorS& p, int idx) { visit([&](double& w) { w = p[idx++]; }); }
     void getParams(VectorS& p, int idx) { visit([&](double& w) { p[idx++] = w; }); }
 
+    // N evaluations on the GPU: in [3][N] = (wz, vx, vy) rows, out [3][N] = (nz, fx, fy) rows; ctx = any libavsim context
+    void forwardBatch(avs_ctx* ctx, int N, const double* in, double* out) {
+        std::vector<double> p;
+        p.reserve(AVS_NUM_BASE_NETWORK_PARAMS);
+        visit([&](double& w) { p.push_back(w); });
+        const int rc = avs_mlp_forward(ctx, AVS_MLP_BASE_NETWORK, p.data(), N, in, out);
+        if (rc != AVS_OK) throw std::runtime_error(std::string("BaseNetwork::forwardBatch: ") + avs_strerror(rc) + " — " + avs_last_error(ctx));
+    }
+
     double m_weight0[8][3], m_bias0[8], m_weight1[8][8], m_bias1[8], m_weight2[3][8], m_bias2[3];
 
 private:
@@ -61,4 +76,21 @@ private:
         for (auto& row : m_weight2) for (double& w : row) f(w);
         for (double& b : m_bias2) f(b);
     }
+};
+
+// data/nn_pretrained.csv: 5-16-16-3 network with biases + output / input scalers (435 numbers; no reference code reads it)
+class LegacyTireNet {
+public:
+    explicit LegacyTireNet(const std::string& csv_path) : m_params(AVS_NUM_LEGACY_NET_PARAMS) {
+        if (avs_load_legacy_net_csv(csv_path.c_str(), m_params.data()) != AVS_OK)
+            throw std::runtime_error("LegacyTireNet: " + csv_path + " does not hold exactly 435 numbers");
+    }
+    const std::vector<double>& params() const { return m_params; }
+    // in [5][N] -> out [3][N] = net((in - in_mean) / in_std) * out_std + out_mean
+    void forwardBatch(avs_ctx* ctx, int N, const double* in, double* out) const {
+        const int rc = avs_mlp_forward(ctx, AVS_MLP_LEGACY_TIRE, m_params.data(), N, in, out);
+        if (rc != AVS_OK) throw std::runtime_error(std::string("LegacyTireNet::forwardBatch: ") + avs_strerror(rc) + " — " + avs_last_error(ctx));
+    }
+private:
+    std::vector<double> m_params;
 };

@@ -410,11 +410,17 @@ def run_b200(args):
         bms, _, bclk = timed(lambda: bk.rollout_dev(Nb, Tf, sub, dbx0.data_ptr(), dbctrl.data_ptr(), 0, dbf.data_ptr()), 2, 1)
         kb_ms, _ = bk.last_kernel_ms()
         finite = bool(torch.isfinite(dbf).all().item())
+        # the same workload with the 10-angle contact search (HybridDynamics::get_tire_cpts_sinkages_fancy) switched on
+        bk.set_contact_search(True)
+        cms, _, _ = timed(lambda: bk.rollout_dev(Nb, Tf, sub, dbx0.data_ptr(), dbctrl.data_ptr(), 0, dbf.data_ptr()), 1, 1)
+        bk.set_contact_search(False)
         if rank == 0:
             extra["configs3_bekker_grid"] = {
                 "workload": f"configs[3] per GPU: {Nb} rollouts x {Tf} rows, Bekker tire model, 512^2 randomised height + per-cell soil grids (65536 rollouts over 8 GPUs)",
                 "value": world * bsteps * 2 / (bms * 1e-3), "unit": UNIT, "n_gpus": world, "scaling": "weak", "ms_per_rollout_batch": bms / 2,
                 "kernel_ms": {"rollout_fwd_kernel<Bekker,dyn>": kb_ms}, "clocks": bclk, "all_finite": finite,
+                "with_contact_search": {"value": world * bsteps / (cms * 1e-3), "unit": UNIT, "ms_per_rollout_batch": cms,
+                                        "what": "same batch, sinkage from the 10-angle contact search (40 height lookups per ODE evaluation instead of 4)"},
                 "roofline": roofline_block(counters, "rollout_fwd_kernel<Bekker,dyn>", bsteps, kb_ms, fp64_peak, hbm_peak)}
         bk.close()
         del dbx0, dbctrl, dbf

@@ -83,6 +83,14 @@ int avs_get_bekker_params(avs_ctx* ctx, double* p5);
 int avs_set_terrain_analytic(avs_ctx* ctx, int kind);
 int avs_set_terrain_grid(avs_ctx* ctx, const double* height, const double* soil, int nx, int ny, double x0, double y0, double dx, double dy);
 
+/* ---- contact model.  0 (default): the contact point lies straight under the hub, as in the reference's ODE
+ *      (HybridDynamics::get_tire_cpts + get_tire_sinkages, HybridDynamics.cpp:214-253).  1: the 10-angle contact search of
+ *      HybridDynamics::get_tire_cpts_sinkages_fancy (HybridDynamics.cpp:258-316, present but not called in the reference): per
+ *      wheel, ten rim points at pitch -0.3 ... +0.3 rad, sinkage = the largest candidate sinkage (>= 0), reported point = the
+ *      joint centre (per-cell soil, where configured, is looked up there).  Forward paths only: avs_rollout_grad returns
+ *      AVS_E_STATE while it is on. */
+int avs_set_contact_search(avs_ctx* ctx, int on);
+
 /* ---- tuning: upper bound in bytes for the reverse-sweep checkpoint buffer (0 = auto: 60 % of free HBM) */
 int avs_set_checkpoint_budget(avs_ctx* ctx, unsigned long long bytes);
 
@@ -164,6 +172,20 @@ int avs_comm_info(const avs_ctx* ctx, int* world, int* rank, int* nccl_version);
 int avs_allreduce_dev(avs_ctx* ctx, double* d_reduced);
 /* host convenience: all-reduce the context's own reduced buffer and (optionally) copy the result to reduced_host_out[418] */
 int avs_allreduce(avs_ctx* ctx, double* reduced_host_out);
+
+/* ---- the reference's two auxiliary networks as batched device functions; in [n_in][N], out [3][N]
+ *      AVS_MLP_BASE_NETWORK: BaseNetwork::forward (src/BaseNetwork.cpp:41-60): (wz, vx, vy) -> (nz, fx, fy); params[131] in the
+ *        reference pack order W0 (8x3), b0, W1 (8x8), b1, W2 (3x8), b2 (src/BaseNetwork.cpp:62-152).  The reference's ODE never
+ *        calls it (HybridDynamics.cpp:433, 557 commented out), so it is not wired into the rollout kernels either.
+ *      AVS_MLP_LEGACY_TIRE: the 5-16-16-3 network + scalers stored in data/nn_pretrained.csv (435 numbers, read by
+ *        avs_load_legacy_net_csv, which tolerates the junk token on line 426): out = net((in - in_mean) / in_std) * out_std +
+ *        out_mean, tanh hidden layers.  No reference code reads that file or defines its five inputs, hence a
+ *        plain function and not a tire model of the ODE. */
+enum { AVS_MLP_BASE_NETWORK = 0, AVS_MLP_LEGACY_TIRE = 1 };
+#define AVS_NUM_BASE_NETWORK_PARAMS 131
+#define AVS_NUM_LEGACY_NET_PARAMS 435
+int avs_load_legacy_net_csv(const char* path, double* params435);
+int avs_mlp_forward(avs_ctx* ctx, int kind, const double* params, int N, const double* in, double* out);
 
 /* ---- pinned (page-locked) host staging for the SoA buffers of the host-pointer entry points
  *      (Trainer::loadDataFile -> windows -> x0 / ctrl / gt, reference src/Trainer.cpp:102-143, 163-165) */

@@ -119,6 +119,7 @@ struct TerrainSpec {
     double x0 = 0, y0 = 0, dx = 1, dy = 1;
     const double* height = nullptr;  // [ny][nx]
     const double* soil = nullptr;    // [5][ny][nx] or null (Bekker soil grids; extension)
+    int contact_search = 0;          // 1: sinkage from HybridDynamics::get_tire_cpts_sinkages_fancy (10-angle contact search)
 };
 
 // Bilinear cell lookup shared by the height and soil grids (extension; the CUDA kernel implements
@@ -617,6 +618,36 @@ template <class S> struct HybridDynamics {
             sinkages[i] = altitude - cpt_pts[i][2];
         }
     }
+    // HybridDynamics::get_tire_cpts_sinkages_fancy (HybridDynamics.cpp:258-316; utils.cpp:5-17 roty): for every wheel, ten
+    // candidate contact points on the rim, at pitch angles -0.3 ... +0.3 rad about the joint axis; the sinkage is the largest
+    // candidate sinkage (0 if none is positive) and the reported point is the JOINT centre.  (Unused by the reference's own
+    // ODE; offered here as an option for rough height fields.)
+    void get_tire_cpts_sinkages_fancy(const S* X, Vec3<S> cpt_pts[4], S sinkages[4]) const {
+        Mat3<S> base_rot = toMatrixRotation(X[0], X[1], X[2], X[3]);
+        const int max_checks = 10;
+        const S max_angle(-.3);
+        for (int ii = 0; ii < 4; ii++) {
+            Vec3<S> e; e[0] = S(tx_w[ii]); e[1] = S(ty_w[ii]); e[2] = S(tz_w[ii]);
+            Vec3<S> r = mul(base_rot, e);
+            Vec3<S> joint;
+            joint[0] = r[0] + X[4]; joint[1] = r[1] + X[5]; joint[2] = r[2] + X[6];
+            cpt_pts[ii] = joint;
+            S max_sinkage(0.0);
+            for (int jj = 0; jj < max_checks; jj++) {
+                S test_angle = max_angle - (2 * max_angle * jj / (S((double)max_checks) - 1));
+                const S sa = s_sin(test_angle), ca = s_cos(test_angle);
+                // test_rot = base_rot * roty(test_angle); test_pos = joint + test_rot * (0, 0, -tire_radius)
+                Vec3<S> test_pos;
+                for (int i = 0; i < 3; i++) {
+                    const S col2 = base_rot.m[i][0] * sa + base_rot.m[i][2] * ca;
+                    test_pos[i] = joint[i] + col2 * (-tire_radius);
+                }
+                const S test_sinkage = getAltitude(terrain, test_pos[0], test_pos[1]) - test_pos[2];
+                if (value(test_sinkage) > value(max_sinkage)) max_sinkage = test_sinkage;
+            }
+            sinkages[ii] = max_sinkage;
+        }
+    }
     // :321-349
     void get_tire_cpt_vels(const S* X, Vec3<S> cpt_vels[4]) const {
         Vec3<S> lin_vel, ang_vel;
@@ -631,9 +662,13 @@ template <class S> struct HybridDynamics {
     // NN: HybridDynamics.cpp:351-417 ; Bekker: BekkerDynamics.cpp:31-120
     void get_tire_f_ext(const S* X, Vec6<S> ext_forces[5]) {
         Vec3<S> cpt_points[4]; Mat3<S> rot;
-        get_tire_cpts(X, cpt_points, rot);
         S sinkages[4];
-        get_tire_sinkages(cpt_points, sinkages);
+        if (terrain.contact_search) {
+            get_tire_cpts_sinkages_fancy(X, cpt_points, sinkages);
+        } else {
+            get_tire_cpts(X, cpt_points, rot);
+            get_tire_sinkages(cpt_points, sinkages);
+        }
         Vec3<S> cpt_vels[4];
         get_tire_cpt_vels(X, cpt_vels);
         for (int ii = 0; ii < 4; ii++) {

@@ -26,13 +26,14 @@ struct orc_terrain {
     double x0, y0, dx, dy;
     const double* height;
     const double* soil;
+    int contact_search;  // 0: contact point under the hub (reference ODE); 1: get_tire_cpts_sinkages_fancy
 };
 
 static TerrainSpec mkTerrain(const orc_terrain* t) {
     TerrainSpec s;
     if (!t) return s;
     s.kind = t->kind; s.nx = t->nx; s.ny = t->ny; s.x0 = t->x0; s.y0 = t->y0; s.dx = t->dx; s.dy = t->dy;
-    s.height = t->height; s.soil = t->soil;
+    s.height = t->height; s.soil = t->soil; s.contact_search = t->contact_search;
     return s;
 }
 
@@ -349,6 +350,15 @@ void orc_rollout_batch_margins(int tire_model, const double* params, const orc_t
         active_margin() = nullptr;
         for (int k = 0; k < NUM_MARGINS; k++) margins[(size_t)k * N + n] = m[k];
     });
+}
+
+// HybridDynamics::get_tire_cpts_sinkages_fancy on one state: sinkages [4], joint centres [4][3]
+void orc_fancy_sinkages(const orc_terrain* t, const double* X21, double* sinkages4, double* pts12) {
+    HybridDynamics<double> dyn;
+    dyn.terrain = mkTerrain(t);
+    Vec3<double> pts[4];
+    dyn.get_tire_cpts_sinkages_fancy(X21, pts, sinkages4);
+    for (int i = 0; i < 4; i++) for (int k = 0; k < 3; k++) pts12[i * 3 + k] = pts[i][k];
 }
 
 int orc_hardware_threads() { return (int)std::thread::hardware_concurrency(); }

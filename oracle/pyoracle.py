@@ -28,12 +28,13 @@ def build(force=False):
 
 class Terrain(C.Structure):
     _fields_ = [("kind", C.c_int), ("nx", C.c_int), ("ny", C.c_int), ("x0", C.c_double), ("y0", C.c_double),
-                ("dx", C.c_double), ("dy", C.c_double), ("height", C.c_void_p), ("soil", C.c_void_p)]
+                ("dx", C.c_double), ("dy", C.c_double), ("height", C.c_void_p), ("soil", C.c_void_p), ("contact_search", C.c_int)]
 
 
-def terrain(kind=FLAT, height=None, soil=None, x0=0.0, y0=0.0, dx=1.0, dy=1.0):
+def terrain(kind=FLAT, height=None, soil=None, x0=0.0, y0=0.0, dx=1.0, dy=1.0, contact_search=0):
     t = Terrain()
     t.kind = kind
+    t.contact_search = int(contact_search)  # 1: HybridDynamics::get_tire_cpts_sinkages_fancy instead of the point under the hub
     t._keep = []
     if kind == GRID:
         h = np.ascontiguousarray(height, dtype=np.float64)
@@ -266,6 +267,38 @@ def rollout_grad_batch(p416, t, x0, ctrl, gt, T, explode_thresh=100.0, explode_m
                                  explode_mode, _p(loss_), _p(gs), C.byref(ls), C.byref(nk),
                                  _p(gps) if per_sample else None, nthreads)
     return loss_, gs, ls.value, nk.value, gps
+
+
+def fancy_sinkages(t, X21):
+    X = _f64(X21)
+    sk, pts = np.zeros(4), np.zeros((4, 3))
+    lib().orc_fancy_sinkages(C.byref(t), _p(X), _p(sk), _p(pts))
+    return sk, pts
+
+
+def base_network_forward(p131, x):
+    """BaseNetwork::forward (src/BaseNetwork.cpp:41-60), numpy restatement: x [3][N] = (wz, vx, vy) -> [3][N] = (nz, fx, fy);
+    p131 = W0 (8x3), b0, W1 (8x8), b1, W2 (3x8), b2 row-major (:62-152)"""
+    p, x = _f64(p131), np.atleast_2d(_f64(x).T).T
+    W0, b0 = p[0:24].reshape(8, 3), p[24:32]
+    W1, b1 = p[32:96].reshape(8, 8), p[96:104]
+    W2, b2 = p[104:128].reshape(3, 8), p[128:131]
+    l0 = np.tanh(W0 @ (x * 0.1) + b0[:, None])
+    l1 = np.tanh(W1 @ l0 + b1[:, None])
+    l2 = W2 @ l1 + b2[:, None]
+    return (np.maximum(l2, 0.0) * (-x)) * 10.0
+
+
+def legacy_net_forward(p435, x):
+    """data/nn_pretrained.csv network (layout of scripts/pretrain.py:20-36): x [5][N] -> [3][N]"""
+    p, x = _f64(p435), _f64(x)
+    W0, b0 = p[0:80].reshape(16, 5), p[80:96]
+    W2, b2 = p[96:352].reshape(16, 16), p[352:368]
+    W4, b4 = p[368:416].reshape(3, 16), p[416:419]
+    out_mean, out_std, in_mean, in_std = p[419:422], p[422:425], p[425:430], p[430:435]
+    s = (x - in_mean[:, None]) / in_std[:, None]
+    h = np.tanh(W2 @ np.tanh(W0 @ s + b0[:, None]) + b2[:, None])
+    return (W4 @ h + b4[:, None]) * out_std[:, None] + out_mean[:, None]
 
 
 def hardware_threads():

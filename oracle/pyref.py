@@ -96,6 +96,21 @@ def fd(base_v6, g6, qd4, fext5x6):
     return a, qdd
 
 
+def fancy_sinkages(terr, X21):
+    """HybridDynamics::get_tire_cpts_sinkages_fancy -> sinkages [4], reported points [4][3]"""
+    X = _f64(X21)
+    sk, pts = np.zeros(4), np.zeros((4, 3))
+    lib().ref_fancy_sinkages(terr, _p(X), _p(sk), _p(pts))
+    return sk, pts
+
+
+def base_network_forward(p131, in3):
+    p, i = _f64(p131), _f64(in3)
+    o = np.zeros(3)
+    lib().ref_base_network_forward(_p(p), _p(i), _p(o))
+    return o
+
+
 def ode(tire, params, terr, X21, u2):
     x = np.concatenate([_f64(X21), _f64(u2)])
     p = _f64(params)

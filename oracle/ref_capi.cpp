@@ -133,6 +133,31 @@ void ref_fd(const double* base_v6, const double* g6, const double* qd4, const do
     for (int i = 0; i < 4; i++) qdd4[i] = CppAD::Value(qdd[i]);
 }
 
+// HybridDynamics::get_tire_cpts_sinkages_fancy (the 10-angle contact search): sinkages [4], reported points [4][3]
+void ref_fancy_sinkages(int terr, const double* X21, double* sinkages4, double* pts12) {
+    HybridDynamics dyn;
+    dyn.setTerrainMap(mkMap(terr));
+    Eigen::Matrix<ADF, 21, 1> X;
+    for (int i = 0; i < 21; i++) X[i] = X21[i];
+    Eigen::Matrix<ADF, 3, 1> pts[4];
+    Eigen::Matrix<ADF, 3, 3> rots[4];
+    ADF sk[4];
+    dyn.get_tire_cpts_sinkages_fancy(X, pts, rots, sk);
+    for (int i = 0; i < 4; i++) { sinkages4[i] = CppAD::Value(sk[i]); for (int k = 0; k < 3; k++) pts12[i * 3 + k] = CppAD::Value(pts[i][k]); }
+}
+
+// BaseNetwork::setParams + forward (src/BaseNetwork.cpp): (wz, vx, vy) -> (nz, fx, fy)
+void ref_base_network_forward(const double* p131, const double* in3, double* out3) {
+    BaseNetwork net;
+    VectorAD p(net.getNumParams());
+    for (int i = 0; i < net.getNumParams(); i++) p[i] = p131[i];
+    net.setParams(p, 0);
+    Eigen::Matrix<ADF, 3, 1> in, out;
+    for (int i = 0; i < 3; i++) in[i] = in3[i];
+    net.forward(in, out);
+    for (int i = 0; i < 3; i++) out3[i] = CppAD::Value(out[i]);
+}
+
 // System::forward: X23 = state + controls -> Xd23
 void ref_ode(int tire, const double* params, int terr, const double* X23, double* Xd23) {
     Quiet q;

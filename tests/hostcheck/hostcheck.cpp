@@ -36,6 +36,7 @@ static void fill_mc(ModelConst& mc, const double* p416, const double* zw152, con
     }
     if (bek5) memcpy(mc.bek, bek5, sizeof(mc.bek));
     compute_AIinv(mc.AIinv);
+    fill_contact_search(mc);
     mc.terr_kind = 0;
     static std::vector<double> ztab;
     if (zw152) { ztab.resize((size_t)kZTabN * (kZTabDeg + 1)); build_ztab(mc.Z0, mc.Z2, mc.Z4, ztab.data()); mc.ztab = ztab.data(); }
@@ -117,7 +118,11 @@ template <int TERR> static void bwd_body(const ModelConst& mc, const RolloutArgs
     rollout_bwd_body(a, n, loss, Scratch<1>{sc}, st, mk);
 }
 
+static int g_contact_search = 0;  // hc_set_contact_search: the TERR_DYN instantiations read ModelConst::contact_search
+
 extern "C" {
+
+void hc_set_contact_search(int on) { g_contact_search = on; }
 
 struct hc_model {
     int tire, terr, nx, ny;
@@ -128,9 +133,16 @@ struct hc_model {
     const double* soil;
 };
 
-static void mk(const hc_model* m, ModelConst& mc) {
+static void mk(const hc_model* m, ModelConst& mc);
+static void mk_base(const hc_model* m, ModelConst& mc) {
     fill_mc(mc, m->tire == 0 ? m->params : nullptr, m->zw, m->tire == 1 ? m->params : nullptr, m->height, m->soil, m->nx, m->ny, m->x0, m->y0,
             m->dx > 0 ? m->dx : 1.0, m->dy > 0 ? m->dy : 1.0);
+}
+
+static void mk(const hc_model* m, ModelConst& mc) {
+    mk_base(m, mc);
+    mc.terr_kind = m->terr;                  // read by the TERR_DYN (= 7) instantiations only
+    mc.contact_search = g_contact_search;
 }
 
 void hc_zweights(double* out152) { memcpy(out152, kFixedZ0, 64); memcpy(out152 + 8, kFixedZ2, 512); memcpy(out152 + 72, kFixedZ4, 64); }
@@ -150,6 +162,7 @@ void hc_bekker_tire(const hc_model* m, double cvx, double cvy, double w, double 
 }
 void hc_ode(const hc_model* m, const double* X13, const double* u2, double* Xd13, const double* ws4) {
     ModelConst mc; mk(m, mc);
+    if (g_contact_search) { if (m->tire == 0) ode13<0, TERR_DYN>(mc, X13, u2, Xd13, ws4); else ode13<1, TERR_DYN>(mc, X13, u2, Xd13, ws4); return; }
     DISPATCH(ode13, m->tire, m->terr, mc, X13, u2, Xd13, ws4);
 }
 void hc_rk4(const hc_model* m, const double* X13, const double* u2, double* Xn13, double* stages52) {
@@ -192,6 +205,10 @@ void hc_rollout(const hc_model* m, int N, int T, int substeps, const double* x0,
     ModelConst mc; mk(m, mc);
     RolloutArgs a; memset(&a, 0, sizeof(a));
     a.N = N; a.Nc = N; a.T = T; a.substeps = substeps; a.x0 = x0; a.ctrl = ctrl; a.x_list = x_list; a.x_final = x_final;
+    if (g_contact_search) {  // the contact search lives in the run-time-terrain instantiation
+        for (int n = 0; n < N; n++) { if (m->tire == 0) fwd_body<0, TERR_DYN>(mc, a, n, false); else fwd_body<1, TERR_DYN>(mc, a, n, false); }
+        return;
+    }
     for (int n = 0; n < N; n++) DISPATCH(fwd_body, m->tire, m->terr, mc, a, n, false);
 }
 // Bekker rollout + branch margins [kNumMargins][N] (same definitions as the kernel's diagnostic instantiation)

@@ -36,6 +36,11 @@ def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
+def set_contact_search(on):
+    """10-angle contact search (run-time-terrain instantiation of the device math) for the following ode / rollout calls"""
+    lib().hc_set_contact_search(1 if on else 0)
+
+
 def zweights():
     z = np.zeros(152)
     lib().hc_zweights(_p(z))

@@ -48,3 +48,21 @@ def test_synth_batch_matches_initialize_state():
 def test_no_gpu_fails_loudly():
     with pytest.raises(capi.AvsError):
         capi.Context(0, capi.TIRE_NN)
+
+
+def test_legacy_net_csv_parser_handles_the_reference_file_quirks():
+    """data/nn_pretrained.csv: 435 numbers on 434 lines, one line carrying the junk token ';in_mean' between two numbers
+    (SURVEY.md 0.3).  The fixture reproduces those quirks with its own numbers; the real file is checked where it is mounted."""
+    import os
+    import numpy as np
+    from auvsl_neural_ode_b200 import capi
+    here = os.path.dirname(os.path.abspath(__file__))
+    q = capi.load_legacy_net_csv(os.path.join(here, "golden", "legacy_net_like.csv"))
+    assert np.array_equal(q, np.load(os.path.join(here, "golden", "legacy_net_like.npy")))
+    ref = "/root/reference/data/nn_pretrained.csv"
+    if os.path.exists(ref):
+        r = capi.load_legacy_net_csv(ref)
+        assert r.size == 435 and r[0] == 1.2790e+02 and r[424] == 285.0602943015066 and r[425] == 0.0 and r[434] == 0.028547002200876626
+    import pytest
+    with pytest.raises(capi.AvsError):
+        capi.load_legacy_net_csv(os.path.join(here, "golden", "legacy_net_like.npy"))

@@ -215,3 +215,35 @@ def test_split_tire_adjoint_matches_layered_adjoint():
             xb2, gW2 = hc.ode_vjp_split(m, X, u, lam)
             np.testing.assert_allclose(xb2, xb, rtol=0, atol=1e-14 * np.abs(xb).max())
             np.testing.assert_array_equal(gW2, gW)
+
+
+def test_contact_search_matches_oracle():
+    """SURVEY.md 8 (f4): HybridDynamics::get_tire_cpts_sinkages_fancy (10 candidate contact angles per wheel) as a forward
+    option, device math vs oracle (whose function is itself pinned to the reference's in tests/test_ref_pinning.py): ODE
+    values and a rollout over the 96^2 height / soil grid for both tire models, and Bumpy terrain for the NN model."""
+    from auvsl_neural_ode_b200 import synth
+    g = synth.make_grid_terrain(n=96)
+    kw = dict(height=g["height"], soil=g["soil"], x0=g["x0"], y0=g["y0"], dx=g["dx"], dy=g["dy"])
+    N, T = 5, 30
+    x0, ctrl, _ = synth.make_batch(N, T, seed=41, z_stable=0.06)
+    x0[4], x0[5] = np.linspace(-1.5, 1.5, N), np.linspace(1.0, -1.0, N)
+    ctrl = np.clip(ctrl, 1, 8)
+    hc.set_contact_search(True)
+    try:
+        for tire, params in ((0, P), (1, po.bekker_default_params())):
+            t = po.terrain(po.GRID, contact_search=1, **kw)
+            m = hc.model(tire, po.GRID, params, **kw)
+            xl, _ = hc.rollout(m, x0, ctrl, T)
+            xl_o, _ = po.rollout_batch(tire, params, t, x0, ctrl, T, nthreads=4)
+            xl_plain, _ = po.rollout_batch(tire, params, po.terrain(po.GRID, **kw), x0, ctrl, T, nthreads=4)
+            err = float(np.max(np.abs(xl - xl_o) / np.maximum(1.0, np.abs(xl_o))))
+            print(f"contact search, tire {tire}: device math vs oracle {err:.2e}; effect of the option on the states {np.abs(xl_o - xl_plain).max():.2e}")
+            assert err < 1e-9
+            assert np.abs(xl_o - xl_plain).max() > 1e-6  # the option does change the result
+        xb = x0.copy()
+        xb[4] = np.linspace(1.9, 3.5, N)
+        xl, _ = hc.rollout(hc.model(0, po.BUMPY, P), xb, ctrl, T)
+        xl_o, _ = po.rollout_batch(0, P, po.terrain(po.BUMPY, contact_search=1), xb, ctrl, T, nthreads=4)
+        assert float(np.max(np.abs(xl - xl_o) / np.maximum(1.0, np.abs(xl_o)))) < 1e-9
+    finally:
+        hc.set_contact_search(False)

@@ -363,6 +363,65 @@ def test_grid_terrain_and_soil(nn, bk):
     bk.set_terrain(capi.FLAT)
 
 
+def test_contact_search_option(nn, bk):
+    """SURVEY.md 8 (f4): the 10-angle contact search of HybridDynamics::get_tire_cpts_sinkages_fancy as a forward option
+    (avs_set_contact_search), on the 96^2 height + soil grid for both tire models and on Bumpy terrain, vs the oracle (whose
+    function is pinned to the reference's own in tests/test_ref_pinning.py); the adjoint refuses to run with it."""
+    g = synth.make_grid_terrain(n=96)
+    kw = dict(height=g["height"], soil=g["soil"], x0=g["x0"], y0=g["y0"], dx=g["dx"], dy=g["dy"])
+    N, T = 40, 30
+    x0, ctrl, gt = synth.make_batch(N, T, seed=41, z_stable=0.06)
+    x0[4], x0[5] = np.linspace(-1.5, 1.5, N), np.linspace(1.0, -1.0, N)
+    ctrl = np.clip(ctrl, 1, 8)
+    t = po.terrain(po.GRID, contact_search=1, **kw)
+    try:
+        for ctx, tire, params in ((nn, po.TIRE_NN, P), (bk, po.TIRE_BEKKER, po.bekker_default_params())):
+            ctx.set_terrain_grid(g["height"], g["soil"], g["x0"], g["y0"], g["dx"], g["dy"])
+            xl_plain, _ = ctx.rollout(x0, ctrl, T)
+            ctx.set_contact_search(True)
+            xl, _ = ctx.rollout(x0, ctrl, T)
+            xl_o, _ = po.rollout_batch(tire, params, t, x0, ctrl, T, nthreads=8)
+            e = rel_state_err(xl, xl_o)
+            print(f"[contact search] tire {tire}: vs oracle {e:.2e}; the option moves the states by up to {np.abs(xl - xl_plain).max():.2e}")
+            assert e < STATE_RTOL and np.abs(xl - xl_plain).max() > 1e-6
+            if tire == po.TIRE_NN:
+                with pytest.raises(capi.AvsError):
+                    ctx.rollout_grad(x0, ctrl, gt, T)
+                ctx.set_terrain(capi.BUMPY)
+                xb = x0.copy()
+                xb[4] = np.linspace(1.9, 3.5, N)
+                xl, _ = ctx.rollout(xb, ctrl, T)
+                xl_o, _ = po.rollout_batch(tire, params, po.terrain(po.BUMPY, contact_search=1), xb, ctrl, T, nthreads=8)
+                assert rel_state_err(xl, xl_o) < STATE_RTOL
+                ctx.set_terrain(capi.FLAT)  # flat terrain + contact search must leave the lean flat kernel
+                xl, _ = ctx.rollout(x0, ctrl, T)
+                xl_o, _ = po.rollout_batch(tire, params, po.terrain(po.FLAT, contact_search=1), x0, ctrl, T, nthreads=8)
+                assert rel_state_err(xl, xl_o) < STATE_RTOL
+            ctx.set_contact_search(False)
+    finally:
+        nn.set_contact_search(False)
+        bk.set_contact_search(False)
+        nn.set_terrain(capi.FLAT)
+        bk.set_terrain(capi.FLAT)
+
+
+def test_auxiliary_networks_on_device(nn):
+    """SURVEY.md 8 (f2): BaseNetwork::forward and the data/nn_pretrained.csv network as batched device functions vs their
+    restatements (BaseNetwork's is pinned to the reference's own class in tests/test_ref_pinning.py)."""
+    rng = np.random.default_rng(8)
+    N = 1000
+    p = rng.normal(0, 0.7, 131)
+    x = rng.normal(0, 2.0, (3, N))
+    np.testing.assert_allclose(nn.mlp_forward(capi.MLP_BASE_NETWORK, p, x), po.base_network_forward(p, x), rtol=1e-12, atol=1e-13)
+    csv = os.path.join(os.path.dirname(__file__), "golden", "legacy_net_like.csv")
+    q = capi.load_legacy_net_csv(csv)
+    assert q.size == 435 and np.array_equal(q, np.load(os.path.join(os.path.dirname(__file__), "golden", "legacy_net_like.npy")))
+    x5 = q[425:430, None] + q[430:435, None] * rng.normal(0, 1.5, (5, N))
+    want = po.legacy_net_forward(q, x5)
+    got = nn.mlp_forward(capi.MLP_LEGACY_TIRE, q, x5)
+    np.testing.assert_allclose(got, want, rtol=1e-11, atol=1e-11 * np.abs(want).max())
+
+
 def test_full_size_properties(nn):
     """BASELINE configs[1]/[2] sizes (N = 4096): the oracle cannot finish these, so check size-independent
     properties: permutation equivariance over the batch, determinism, agreement of a strided sample with the

@@ -127,6 +127,28 @@ def test_ode_and_integrate_match(tire):
     assert worst_ode < 1e-11 and worst_int < 1e-12
 
 
+def test_contact_search_function_matches():
+    """HybridDynamics::get_tire_cpts_sinkages_fancy (HybridDynamics.cpp:258-316), the reference's own function vs the restatement"""
+    worst = 0.0
+    for terr in (0, 1, 2):
+        for _ in range(25):
+            X, _ = random_state(0.055 + RNG.normal(0, 0.01))
+            if terr == 1:
+                X[6] += 0.1 * X[4]
+            a, pa = pr.fancy_sinkages(terr, X)
+            b, pb = po.fancy_sinkages(po.terrain(terr), X)
+            worst = max(worst, float(np.abs(a - b).max()), float(np.abs(pa - pb).max()))
+    assert worst < 1e-14, worst
+
+
+def test_base_network_forward_matches():
+    """BaseNetwork::forward (dead code in the reference's ODE, kept as API surface): the reference's own class vs the numpy restatement"""
+    for _ in range(20):
+        p = RNG.normal(0, 0.7, 131)
+        x = RNG.normal(0, 2.0, 3)
+        np.testing.assert_allclose(po.base_network_forward(p, x[:, None])[:, 0], pr.base_network_forward(p, x), rtol=1e-13, atol=1e-15)
+
+
 def test_settle_and_adapters_match():
     for tire in (0, 1):
         P = pr.default_params(tire)
