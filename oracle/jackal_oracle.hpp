@@ -1,4 +1,6 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY.  Parity status: "parity unpinned".
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Parity status: pinned to the reference's own first-party sources, compiled in place behind
+// restated third-party headers (oracle/_ref, oracle/refshim/; tests/test_ref_pinning.py) — see oracle/README.md for what that
+// does and does not claim.
 // CPU restatement of the reference's batched-rollout hot path, templated on the scalar type
 // (double / orc::Rev / orc::Dual / orc::Cnt, see scalar.hpp).  It follows the reference
 // statement by statement, INCLUDING its dense "wasteful" order (6x6 products with constant
@@ -13,7 +15,8 @@
 //   Eigen3 (CMakeLists.txt:4,29): dense products, LLT solve
 //   CppAD (src/types/Scalars.h:4-11): CondExp*, abs, pow, tanh, atan2, ADFun::Reverse
 // The reference's tests pin no numeric golden vectors for this path; the loose
-// physical known-answer tests that do exist are re-run on this oracle in tests/test_oracle_kat.py.
+// physical known-answer tests that do exist are re-run on this oracle in tests/test_oracle.py, and every function below is
+// compared with the reference's own code (compiled from /root/reference where it lies) in tests/test_ref_pinning.py.
 #pragma once
 #include <cstddef>
 #include <vector>

@@ -1,6 +1,6 @@
 """ctypes binding of the CPU oracle (oracle/_build/liboracle.so).
 
-TEST INFRASTRUCTURE ONLY ("parity unpinned", see oracle/jackal_oracle.hpp).  Importable from
+TEST INFRASTRUCTURE ONLY (parity status: oracle/README.md).  Importable from
 tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs — never from
 the product package auvsl_neural_ode_b200.
 """

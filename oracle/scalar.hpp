@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY.  Parity status: "parity unpinned" (see oracle/README.md).
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Parity status: see oracle/README.md (pinned to the reference's own sources via oracle/_ref).
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 // use anything under oracle/.  The product path (auvsl_neural_ode_b200/csrc) never includes it.
 //

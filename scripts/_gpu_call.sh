@@ -1,2 +1,4 @@
-python -m pytest tests/test_gpu_multi.py -x -q -s > gpurun_out/r2_gpumulti.log 2>&1; echo "pytest rc=$?"; tail -8 gpurun_out/r2_gpumulti.log
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29655 bench.py --gpus 2 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_r2_2gpu.json 2> gpurun_out/bench_r2_2gpu.err; echo "bench2 rc=$?"; head -c 300 gpurun_out/bench_r2_2gpu.json; echo; wc -l gpurun_out/bench_r2_2gpu.json
+python -m pytest tests -m gpu -x -q -s > gpurun_out/r2_gputest3.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/r2_gputest3.log; grep "contact search\]" gpurun_out/r2_gputest3.log
+python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_r2c.json 2> gpurun_out/bench_r2c.err; echo "bench rc=$?"; tail -2 gpurun_out/bench_r2c.err
+python -c "
+import json; d=json.load(open('gpurun_out/bench_r2c.json')); b=d['configs3_bekker_grid']; print(b['value'], b['kernel_ms'], b['with_contact_search'])"
