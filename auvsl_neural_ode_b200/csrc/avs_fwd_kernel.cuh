@@ -9,7 +9,7 @@ namespace avs {
 // more serial order (measured: forward+store 14.1 ms vs 11.5 ms at N = 4096 x T = 200); with 2 it is 12.1 ms.
 // MARGIN (Bekker only): diagnostic instantiation that also reports the branch margins of every trajectory (avs_bekker.cuh)
 template <int TIRE, int TERR, bool STORE, bool MARGIN = false>
-__global__ void __launch_bounds__(kFwdBlock, (TIRE == TIRE_NN ? 3 : 0)) rollout_fwd_kernel(const __grid_constant__ RolloutArgs a) {
+__global__ void __launch_bounds__(kFwdBlock, (TIRE == TIRE_NN ? 3 * (128 / kFwdBlock) : 0)) rollout_fwd_kernel(const __grid_constant__ RolloutArgs a) {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     int n = gid >> 2;
     const int lane0 = gid & 3;

@@ -5,7 +5,10 @@
 
 namespace avs {
 
-constexpr int kFwdBlock = 128;  // threads per CTA, forward rollout
+#ifndef AVS_FWD_BLOCK
+#define AVS_FWD_BLOCK 128
+#endif
+constexpr int kFwdBlock = AVS_FWD_BLOCK;  // threads per CTA, forward rollout (scratch columns are per thread: any multiple of 32 works)
 constexpr int kBwdBlock = 32;   // (vehicle, wheel) lanes per CTA of the reverse sweep; the CTA has 2 warps (producer + consumer), 44.5 KB smem, 4 CTAs per SM
 
 // forward rollout: one vehicle per 4-lane group (lane = wheel)
