@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd2_kernel(const __grid_
         auto mk_odeb = [lane0, &stage_counter](double ul, double ur) {
             return OdeBwdCall2<TERR, kBwdBlock>{lane0, 42, 56, 0, kB2SlotJ, kB2SlotF, ul, ur, &stage_counter};
         };
-        CkptStreamRec<kBwdBlock> st{a.ckpt + ((size_t)nrec * a.Nc + n) * kCkRows, (size_t)a.Nc * kCkRows, nrec, 42, 56, 0};
+        CkptStreamRec<kBwdBlock> st{a.ckpt + ((size_t)nrec * a.Nc + n) * kCkRows, (size_t)a.Nc * kCkRows, nrec, 42, 56, 0, a.ckpt, a.ckpt_doubles};
         st.init();
         rollout_bwd_body(a, n, loss, pair_col<kBwdBlock>(0), st, mk_odeb);
         if (writer) a.loss[n] = loss;
@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd2_kernel(const __grid_
         auto prefetch = [&](long j, int t) {  // activation record of reverse stage j -> tile t
             if (j < nrec) {
                 const double* src = act_last - (size_t)j * astride;
+                AVS_DBG_RANGE("activation record (reverse prefetch)", src, 9 * kActPairStride + 2, a.act, a.act_doubles);
                 double* dst = tile_of(t);
 #pragma unroll
                 for (int i = 0; i < kActLen / 2; i++) {

@@ -482,6 +482,7 @@ static int rollout_grad_impl(avs_ctx* ctx, int N, int T, int substeps, const dou
         memset(&a, 0, sizeof(a));
         a.N = N; a.Nc = (int)cnt; a.T = T; a.substeps = substeps;
         a.x0 = d_x0 + begin; a.ctrl = d_ctrl + begin; a.gt = d_gt + begin; a.ckpt = ctx->ckpt.as<double>(); a.act = ctx->act.as<double>();
+        a.ckpt_doubles = ctx->ckpt.cap / 8; a.act_doubles = ctx->act.cap / 8;
         a.loss = d_loss + begin; a.gps = d_grad_live + begin;
         LAUNCH(launch_rollout_fwd(AVS_TIRE_NN, ctx->terr, true, ctx->mc, live(ctx), a, ctx->stream));
         if (begin == 0 && cnt == n) CK(cudaEventRecord(ctx->ev[1], ctx->stream));

@@ -134,6 +134,10 @@ template <int TERR, int BLOCK, bool STORE> struct FusedStep {
         double* act = STORE ? a.act + (step * 4) * act_stride + act_lane_offset((size_t)blockIdx.x * BLOCK + threadIdx.x) : nullptr;
         const size_t rec_stride = NK * kCkRows;
         const int tid = (int)threadIdx.x;
+        if (STORE) {
+            AVS_DBG_RANGE("state records of a step (store)", rec, 3 * rec_stride + kCkRows, a.ckpt, a.ckpt_doubles);
+            AVS_DBG_RANGE("activation records of a step (store)", act, 3 * act_stride + 9 * kActPairStride + 2, a.act, a.act_doubles);
+        }
 #pragma unroll 1
         for (int s = 0; s < 4; s++)
             ode_fwd_stage_call<TERR, BLOCK, STORE>(tid, lane0, ul, ur, s, rec ? rec + (size_t)s * rec_stride : nullptr, STORE ? act + (size_t)s * act_stride : nullptr);
@@ -252,11 +256,13 @@ template <int BLOCK> struct CkptStreamRec {
     size_t rec_stride;
     long remaining;
     int slotA, slotB, parity;
+    const double* dbg_base; size_t dbg_total;  // extent of the state-record buffer (AVS_DEBUG)
     __device__ __forceinline__ const double* act() const { return nullptr; }
     __device__ __forceinline__ PairCol<BLOCK> cur() const { return pair_col<BLOCK>(parity ? slotB : slotA); }
     __device__ __forceinline__ void prefetch_prev() {
         if (remaining <= 0) return;
         const double* src = rec - rec_stride;
+        AVS_DBG_RANGE("state record (reverse prefetch)", src, kCkRows, dbg_base, dbg_total);
         const int slot = parity ? slotA : slotB;
 #pragma unroll
         for (int i = 0; i < kCkRows / 2; i++) {
@@ -266,6 +272,7 @@ template <int BLOCK> struct CkptStreamRec {
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
     __device__ __forceinline__ void init() {
+        AVS_DBG_RANGE("final state record (reverse init)", rec, kCkRows, dbg_base, dbg_total);
         const PairCol<BLOCK> dst = cur();
 #pragma unroll
         for (int c = 0; c < kCkRows; c++) dst[c] = __ldg(rec + c);

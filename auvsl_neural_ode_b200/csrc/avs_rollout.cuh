@@ -37,7 +37,25 @@ struct RolloutArgs {
     double* loss;
     double* gps;
     double* margin;  // [kNumMargins][N] branch margins (diagnostic Bekker rollout only) or nullptr
+    size_t ckpt_doubles, act_doubles;  // extents of ckpt / act (checked by the AVS_DEBUG build on every record access)
 };
+
+// AVS_DEBUG build (make debug -> libavsim_debug.so): every address formed on the two record streams is checked against the
+// extent of its buffer; a violation prints the site and traps.  compute-sanitizer is closed on the development pool, so this
+// is the index check the hand-rolled stream arithmetic gets (tests/test_gpu_soak.py runs the all-kernels case on this build).
+#if defined(AVS_DEBUG) && defined(__CUDA_ARCH__)
+#define AVS_DBG_RANGE(what, ptr, len, base, total)                                                                         \
+    do {                                                                                                                   \
+        const double* p__ = (const double*)(ptr);                                                                          \
+        if (p__ && !(p__ >= (const double*)(base) && p__ + (len) <= (const double*)(base) + (total))) {                     \
+            printf("AVS_DEBUG: %s out of range: offset %lld, length %d, extent %llu (block %d thread %d)\n", what,         \
+                   (long long)(p__ - (const double*)(base)), (int)(len), (unsigned long long)(total), blockIdx.x, threadIdx.x); \
+            __trap();                                                                                                      \
+        }                                                                                                                  \
+    } while (0)
+#else
+#define AVS_DBG_RANGE(what, ptr, len, base, total) do { } while (0)
+#endif
 
 AVS_HD double ld(const double* p) {
 #if defined(__CUDA_ARCH__)
@@ -151,7 +169,11 @@ AVS_HD void rollout_fwd_body(const RolloutArgs& a, int n, int lane0, bool valid,
             row[(size_t)21 * N] = 0.0; row[(size_t)22 * N] = 0.0;  // VehicleSystem.cpp:144-147
         }
     }
-    if (STORE && writer) CkptSink::ckpt_store(a.ckpt + (((size_t)(a.T - 1) * a.substeps * 4) * NK + n) * kCkRows, X, inv_carry);
+    if (STORE && writer) {
+        double* last = a.ckpt + (((size_t)(a.T - 1) * a.substeps * 4) * NK + n) * kCkRows;
+        AVS_DBG_RANGE("final state record (store)", last, kCkRows, a.ckpt, a.ckpt_doubles);
+        CkptSink::ckpt_store(last, X, inv_carry);
+    }
     if (a.x_final && writer) {
 #pragma unroll
         for (int c = 0; c < 13; c++) a.x_final[(size_t)live_to_ref(c) * N + n] = X[c];

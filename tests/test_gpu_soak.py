@@ -48,6 +48,37 @@ def test_sanitize_case_runs_clean():
     assert "sanitize case ok" in out.stdout and "True" in out.stdout
 
 
+@pytest.mark.timeout(600)
+def test_index_checked_build_runs_clean():
+    """libavsim_debug.so (make -C auvsl_neural_ode_b200/csrc debug; -DAVS_DEBUG=1) checks every address formed on the state- and
+    activation-record streams against the extent of its buffer and traps on a violation.  The all-kernels case and a set of
+    awkward shapes (tail lanes, chunked batches) must run clean on it and give the production build's results bit for bit."""
+    dbg = os.path.join(ROOT, "auvsl_neural_ode_b200", "libavsim_debug.so")
+    if not os.path.exists(dbg):
+        pytest.skip("libavsim_debug.so not built")
+    env = dict(os.environ, AVS_LIB=dbg)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "sanitize_case.py")], capture_output=True, text=True, timeout=280, env=env)
+    assert out.returncode == 0 and "AVS_DEBUG" not in out.stdout + out.stderr, out.stdout[-2000:] + out.stderr[-2000:]
+    code = (
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "from auvsl_neural_ode_b200 import capi, synth\n"
+        "ctx = capi.Context(0, capi.TIRE_NN)\n"
+        "acc = []\n"
+        "for N, T, sub in ((1, 2, 1), (7, 3, 10), (33, 17, 7), (257, 9, 10), (600, 6, 10)):\n"
+        "    x0, ctrl, gt = synth.make_batch(N, T, seed=N)\n"
+        "    if N == 600: ctx.set_checkpoint_budget((((T - 1) * sub * 4 + 1) * 14 * 8 + (T - 1) * sub * 4 * 20 * 4 * 8) * 256 + 64)\n"
+        "    loss, red, gps = ctx.rollout_grad(x0, ctrl, gt, T, substeps=sub)\n"
+        "    acc.append(float(loss.sum()) + float(np.abs(gps).sum()))\n"
+        "print('RESULT', repr(acc))\n")
+    res = {}
+    for tag, e in (("debug", env), ("production", dict(os.environ))):
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=280, env=e)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        res[tag] = [l for l in r.stdout.splitlines() if l.startswith("RESULT")][0]
+    assert res["debug"] == res["production"]
+
+
 def test_two_contexts_on_one_device_do_not_race():
     """Every translation unit keeps ONE __constant__ model per device; two contexts with different weights used through the
     asynchronous *_dev entry points on their own streams must each see their own model (launches are serialised against the
