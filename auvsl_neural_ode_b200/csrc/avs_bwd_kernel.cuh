@@ -19,15 +19,18 @@
 namespace avs {
 
 constexpr int kBwdThreads = 2 * kBwdBlock;  // producer warp + consumer warp
+#ifndef AVS_BWD_STAGGER
+#define AVS_BWD_STAGGER 0
+#endif
 
 // ---- split tire adjoint ------------------------------------------------------------------------------------------------
 // Same two roles, different cut: the producer's state chain uses the xy-net Jacobian the consumer formed a stage ahead
 // (3x3 worth of FMAs instead of the layered back-propagation, 5 staged values instead of 37, no activation traffic), the
 // consumer owns the activation stream (own cp.async ring, three tiles deep), forms J, runs the layered back-propagation for
 // the weight gradient and accumulates the outer products.
-// scratch columns (16-byte pairs, 14 slots per 13-vector): LAM 0 | YB 14 | KB 28 | record A 42 | record B 56 |
-// activation tiles 70 (3 x kActLen) | J ring | F ring | dW4
-constexpr int kB2SlotT = 70, kB2SlotJ = kB2SlotT + 3 * kActLen, kB2SlotF = kB2SlotJ + 2 * kJLen, kB2SlotG4 = kB2SlotF + 2 * kFLen, kB2Slots = kB2SlotG4 + 16;  // + dW4 accumulators (16 per lane, as 8 pairs)
+// scratch columns (16-byte pairs, 14 slots per 13-vector): LAM 0 | YB 14 | KB 28 | state tile A 42 | state tile B 46
+// (kCkTile = 112 doubles = 3.5 columns each) | activation tiles 50 (3 x kActLen) | J ring | F ring | dW4
+constexpr int kB2SlotRecA = 42, kB2SlotRecB = 46, kB2SlotT = 50, kB2SlotJ = kB2SlotT + 3 * kActLen, kB2SlotF = kB2SlotJ + 2 * kJLen, kB2SlotG4 = kB2SlotF + 2 * kFLen, kB2Slots = kB2SlotG4 + 16;  // + dW4 accumulators (16 per lane, as 8 pairs)
 
 template <int TERR>
 __global__ void __launch_bounds__(kBwdThreads) rollout_bwd2_kernel(const __grid_constant__ RolloutArgs a) {
@@ -39,14 +42,30 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd2_kernel(const __grid_
     if (!valid) n = a.Nc - 1;
     const bool writer = valid && lane0 == 0;
     const long nrec = (long)(a.T - 1) * a.substeps * 4;
+#if AVS_BWD_STAGGER > 0
+    {   // CTAs in hardware warp slots 4..7 share their two schedulers with the CTAs in slots 0..3 (measured: slot % 4 = scheduler,
+        // a 2-warp CTA takes two consecutive slots).  All CTAs run the same stage loop in near lock-step, so the FP64-dense and the
+        // latency-bound phases of the two warps on a scheduler coincide; starting the second pair part of a stage later
+        // de-correlates them.
+        unsigned wid;
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+        if (wid & 4u) {
+            const long long t0 = clock64();
+            while (clock64() - t0 < AVS_BWD_STAGGER) {}
+        }
+    }
+#endif
     if (threadIdx.x < kBwdBlock) {
         // ---------------- producer warp: state adjoint
         double loss;
         int stage_counter = 0;
-        auto mk_odeb = [lane0, &stage_counter](double ul, double ur) {
-            return OdeBwdCall2<TERR, kBwdBlock>{lane0, 42, 56, 0, kB2SlotJ, kB2SlotF, ul, ur, &stage_counter};
+        const int voff = 2 * (n % kCkTileVeh);  // this lane's vehicle inside the CTA's state tile (tail lanes: the mirrored vehicle)
+        auto mk_odeb = [lane0, voff, &stage_counter](double ul, double ur) {
+            return OdeBwdCall2<TERR, kBwdBlock>{lane0, voff, kB2SlotRecA, kB2SlotRecB, 0, kB2SlotJ, kB2SlotF, ul, ur, &stage_counter};
         };
-        CkptStreamRec<kBwdBlock> st{a.ckpt + ((size_t)nrec * a.Nc + n) * kCkRows, (size_t)a.Nc * kCkRows, nrec, 42, 56, 0, a.ckpt, a.ckpt_doubles};
+        static_assert(kBwdBlock == 4 * kCkTileVeh, "a reverse CTA serves exactly one state tile");
+        const size_t rstride = ck_rec_stride(a.Nc);
+        CkptStreamRec<kBwdBlock> st{a.ckpt + (size_t)nrec * rstride + (size_t)blockIdx.x * kCkTile, rstride, nrec, kB2SlotRecA, kB2SlotRecB, 0, voff, a.ckpt, a.ckpt_doubles};
         st.init();
         rollout_bwd_body(a, n, loss, pair_col<kBwdBlock>(0), st, mk_odeb);
         if (writer) a.loss[n] = loss;

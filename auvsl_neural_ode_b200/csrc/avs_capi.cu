@@ -48,7 +48,7 @@ struct avs_ctx {
     double* d_params = nullptr;  // [416] device copy (RMSProp operates here)
     double* d_sq = nullptr;      // [416] RMSProp state
     bool params_dirty_on_device = false;
-    DevBuf grid_h, grid_s, ztab;
+    DevBuf grid_h, grid_s, ztab, exptab;
     DevBuf ckpt, act, gps, loss, reduced, flags, settle;
     DevBuf in_x0, in_ctrl, in_gt, out_list, out_final, io_a, io_b, io_c;
     DevBuf margins;
@@ -242,11 +242,17 @@ int avs_create(avs_ctx** out, int device, int tire_model) {
     ok = ok && cudaMalloc(&ctx->d_params, sizeof(double) * AVS_NUM_NN_PARAMS) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_sq, sizeof(double) * AVS_NUM_NN_PARAMS) == cudaSuccess;
     if (ok) {  // constant-fold the fixed z-network into its table
-        std::vector<double> tab((size_t)kZTabN * (kZTabDeg + 1));
+        std::vector<double> tab((size_t)kZTabRows * kZTabRow);
         build_ztab(ctx->mc.Z0, ctx->mc.Z2, ctx->mc.Z4, tab.data());
         ok = ctx->ztab.reserve(tab.size() * sizeof(double)) == cudaSuccess &&
              cudaMemcpy(ctx->ztab.p, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess;
         ctx->mc.ztab = ctx->ztab.as<double>();
+    }
+    if (ok) {  // exponential table of the 8-wide tanh
+        double tab[32];
+        build_exptab(tab);
+        ok = ctx->exptab.reserve(sizeof(tab)) == cudaSuccess && cudaMemcpy(ctx->exptab.p, tab, sizeof(tab), cudaMemcpyHostToDevice) == cudaSuccess;
+        ctx->mc.exptab = ctx->exptab.as<double>();
     }
     if (!ok) { avs_destroy(ctx); return AVS_E_CUDA; }
     if (cudaMemcpy(ctx->d_params, ctx->params, sizeof(ctx->params), cudaMemcpyHostToDevice) != cudaSuccess) { avs_destroy(ctx); return AVS_E_CUDA; }
@@ -260,7 +266,7 @@ void avs_destroy(avs_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->comm && nccl_api()->CommDestroy) nccl_api()->CommDestroy(ctx->comm);
     ctx->margins.release();
-    DevBuf* bufs[] = {&ctx->grid_h, &ctx->grid_s, &ctx->ztab, &ctx->ckpt, &ctx->act, &ctx->gps, &ctx->loss, &ctx->reduced, &ctx->flags, &ctx->settle,
+    DevBuf* bufs[] = {&ctx->grid_h, &ctx->grid_s, &ctx->ztab, &ctx->exptab, &ctx->ckpt, &ctx->act, &ctx->gps, &ctx->loss, &ctx->reduced, &ctx->flags, &ctx->settle,
                       &ctx->in_x0, &ctx->in_ctrl, &ctx->in_gt, &ctx->out_list, &ctx->out_final, &ctx->io_a, &ctx->io_b, &ctx->io_c};
     for (DevBuf* b : bufs) b->release();
     if (ctx->d_params) cudaFree(ctx->d_params);
@@ -453,7 +459,7 @@ static int rollout_grad_impl(avs_ctx* ctx, int N, int T, int substeps, const dou
     const size_t n = (size_t)N;
     if (!d_loss) { CK(ctx->loss.reserve(n * 8)); d_loss = ctx->loss.as<double>(); }
     if (!d_grad_live) { CK(ctx->gps.reserve((size_t)kNumLive * n * 8)); d_grad_live = ctx->gps.as<double>(); }
-    // reverse-sweep buffers: (S*4 + 1) state records of 14 doubles + S*4 x 4 wheels activation records of 20 doubles per vehicle; process the batch in chunks if it does not fit the budget
+    // reverse-sweep buffers: (S*4 + 1) state records of 14 doubles (tiled by 8 vehicles) + S*4 x 4 wheels activation records of 20 doubles per vehicle; process the batch in chunks if it does not fit the budget
     const size_t per_vehicle_ck = ((size_t)(T - 1) * substeps * 4 + 1) * kCkRows * 8;
     const size_t per_vehicle_act = (size_t)(T - 1) * substeps * 4 * kActLen * 4 * 8;  // + tile padding, see act_bytes below
     const size_t per_vehicle = per_vehicle_ck + per_vehicle_act;
@@ -473,7 +479,7 @@ static int rollout_grad_impl(avs_ctx* ctx, int N, int T, int substeps, const dou
         ctx->plan_N = N; ctx->plan_per_vehicle = per_vehicle; ctx->plan_budget = ctx->ckpt_budget; ctx->plan_chunk = chunk;
     }
     if (chunk == 0) return fail(ctx, AVS_E_NOMEM, "avs_rollout_grad: the reverse-sweep buffers of one 256-vehicle chunk (%zu B) exceed the memory budget", per_vehicle * 256);
-    CK(ctx->ckpt.reserve(chunk * per_vehicle_ck));
+    CK(ctx->ckpt.reserve(((size_t)(T - 1) * substeps * 4 + 1) * ck_rec_stride(chunk) * 8));  // whole 8-vehicle state tiles
     CK(ctx->act.reserve((size_t)(T - 1) * substeps * 4 * act_stage_doubles(chunk) * 8));  // warp-tiled, padded to whole forward CTAs
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     for (size_t begin = 0; begin < n; begin += chunk) {

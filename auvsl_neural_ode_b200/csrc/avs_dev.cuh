@@ -127,15 +127,15 @@ template <int TERR, int BLOCK, bool STORE> struct FusedStep {
     double ul, ur;
     __device__ __forceinline__ void operator()(size_t step, double& inv_carry) const {
         const size_t NK = (size_t)a.Nc;
-        double* rec = (STORE && writer) ? a.ckpt + ((step * 4) * NK + n) * kCkRows : nullptr;
+        const size_t rec_stride = ck_rec_stride(NK);
+        double* rec = (STORE && writer) ? a.ckpt + (step * 4) * rec_stride + ck_lane_offset(n) : nullptr;
         // activation records: warp-tiled (avs_model.cuh, ActOutPtr); addressed by the thread's own global lane index, so
         // tail lanes (which mirror the last vehicle) write into the padding of the last tile
         const size_t act_stride = act_stage_doubles(NK);
         double* act = STORE ? a.act + (step * 4) * act_stride + act_lane_offset((size_t)blockIdx.x * BLOCK + threadIdx.x) : nullptr;
-        const size_t rec_stride = NK * kCkRows;
         const int tid = (int)threadIdx.x;
         if (STORE) {
-            AVS_DBG_RANGE("state records of a step (store)", rec, 3 * rec_stride + kCkRows, a.ckpt, a.ckpt_doubles);
+            AVS_DBG_RANGE("state records of a step (store)", rec, 3 * rec_stride + 6 * kCkPairStride + 2, a.ckpt, a.ckpt_doubles);
             AVS_DBG_RANGE("activation records of a step (store)", act, 3 * act_stride + 9 * kActPairStride + 2, a.act, a.act_doubles);
         }
 #pragma unroll 1
@@ -207,10 +207,15 @@ template <int BLOCK> struct FOutSmem {
         bar_arrive64(kBarFull + q);
     }
 };
+// state tile staged in shared memory exactly as it lies in HBM (kCkTile doubles, pair r of vehicle v at r*16 + v*2): the four
+// lanes of a vehicle read the same 16 bytes (broadcast), a warp's LDS.128 touches one 128-byte line
+typedef PairCol<kCkTileVeh> RecCol;
+template <int BLOCK> __device__ __forceinline__ RecCol rec_col(int slot, int voff /* 2 * (vehicle % 8) */) { return RecCol{g_smem + (size_t)slot * BLOCK + voff}; }
 template <int TERR, int BLOCK>
-__device__ __noinline__ void ode_bwd_call2(int lane0, int slotXS, int slotLAM, int slotJ, int slotF, double ul, double ur, int stage_count, int s) {
-    // all loop-carried vectors are 16-byte pairs (LDS.128 / STS.128): record | LAM | YB | KB, 14 slots each
-    const PairCol<BLOCK> XS = pair_col<BLOCK>(slotXS), LAM = pair_col<BLOCK>(slotLAM), YB = pair_col<BLOCK>(slotLAM + 14), KB = pair_col<BLOCK>(slotLAM + 28);
+__device__ __noinline__ void ode_bwd_call2(int lane0, int voff, int slotXS, int slotLAM, int slotJ, int slotF, double ul, double ur, int stage_count, int s) {
+    // all loop-carried vectors are 16-byte pairs (LDS.128 / STS.128): LAM | YB | KB, 14 slots each; XS = the staged state tile
+    const RecCol XS = rec_col<BLOCK>(slotXS, voff);
+    const PairCol<BLOCK> LAM = pair_col<BLOCK>(slotLAM), YB = pair_col<BLOCK>(slotLAM + 14), KB = pair_col<BLOCK>(slotLAM + 28);
     JInSmem<BLOCK> jin{g_smem + (size_t)slotJ * BLOCK + (size_t)threadIdx.x * 2, stage_count};
     FOutSmem<BLOCK> fout{g_smem + (size_t)slotF * BLOCK + threadIdx.x, stage_count};
     double X[14], kb[14], Xb[14];
@@ -242,44 +247,48 @@ __device__ __noinline__ void ode_bwd_call2(int lane0, int slotXS, int slotLAM, i
     }
 }
 template <int TERR, int BLOCK> struct OdeBwdCall2 {
-    int lane0, slotXA, slotXB, slotLAM, slotJ, slotF;
+    int lane0, voff, slotXA, slotXB, slotLAM, slotJ, slotF;
     double ul, ur;
     int* stage_counter;
-    template <class V> __device__ __forceinline__ void operator()(PairCol<BLOCK> XS, V, V, V, int s, const double*) const {
-        const bool isA = XS.base == pair_col<BLOCK>(slotXA).base;
-        ode_bwd_call2<TERR, BLOCK>(lane0, isA ? slotXA : slotXB, slotLAM, slotJ, slotF, ul, ur, (*stage_counter)++, s);
+    template <class V> __device__ __forceinline__ void operator()(RecCol XS, V, V, V, int s, const double*) const {
+        const bool isA = XS.base == rec_col<BLOCK>(slotXA, voff).base;
+        ode_bwd_call2<TERR, BLOCK>(lane0, voff, isA ? slotXA : slotXB, slotLAM, slotJ, slotF, ul, ur, (*stage_counter)++, s);
     }
 };
-// state-record stream only (the producer of the split kernel never touches the activation records)
+// state-record stream only (the producer of the split kernel never touches the activation records).  One record of the
+// warp's 8 vehicles = one contiguous kCkTile-double state tile: lanes 0..31 fetch its first 512 bytes, lanes 0..23 the other
+// 384 (two coalesced cp.async instead of seven 16-byte gathers per lane that cost 32 shared-memory wavefronts each); every
+// lane then reads the pairs of ITS vehicle, which other lanes fetched — hence the __syncwarp after the wait.
 template <int BLOCK> struct CkptStreamRec {
-    const double* rec;
+    const double* rec;   // current tile record in HBM
     size_t rec_stride;
     long remaining;
-    int slotA, slotB, parity;
+    int slotA, slotB, parity, voff;
     const double* dbg_base; size_t dbg_total;  // extent of the state-record buffer (AVS_DEBUG)
     __device__ __forceinline__ const double* act() const { return nullptr; }
-    __device__ __forceinline__ PairCol<BLOCK> cur() const { return pair_col<BLOCK>(parity ? slotB : slotA); }
+    __device__ __forceinline__ RecCol cur() const { return rec_col<BLOCK>(parity ? slotB : slotA, voff); }
     __device__ __forceinline__ void prefetch_prev() {
         if (remaining <= 0) return;
         const double* src = rec - rec_stride;
-        AVS_DBG_RANGE("state record (reverse prefetch)", src, kCkRows, dbg_base, dbg_total);
-        const int slot = parity ? slotA : slotB;
-#pragma unroll
-        for (int i = 0; i < kCkRows / 2; i++) {
-            const unsigned saddr = (unsigned)__cvta_generic_to_shared(g_smem + (size_t)slot * BLOCK + ((size_t)i * BLOCK + threadIdx.x) * 2);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(src + 2 * i) : "memory");
-        }
+        AVS_DBG_RANGE("state tile (reverse prefetch)", src, kCkTile, dbg_base, dbg_total);
+        const int lane = threadIdx.x & 31;
+        double* dst = g_smem + (size_t)(parity ? slotA : slotB) * BLOCK;
+        const unsigned s0 = (unsigned)__cvta_generic_to_shared(dst + lane * 2);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0), "l"(src + lane * 2) : "memory");
+        if (lane < kCkTile / 2 - 32) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + 512u), "l"(src + 64 + lane * 2) : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
     __device__ __forceinline__ void init() {
-        AVS_DBG_RANGE("final state record (reverse init)", rec, kCkRows, dbg_base, dbg_total);
-        const PairCol<BLOCK> dst = cur();
-#pragma unroll
-        for (int c = 0; c < kCkRows; c++) dst[c] = __ldg(rec + c);
+        AVS_DBG_RANGE("final state tile (reverse init)", rec, kCkTile, dbg_base, dbg_total);
+        const int lane = threadIdx.x & 31;
+        double* dst = g_smem + (size_t)(parity ? slotB : slotA) * BLOCK;
+        for (int c = lane; c < kCkTile; c += 32) dst[c] = __ldg(rec + c);
+        __syncwarp();
         prefetch_prev();
     }
     __device__ __forceinline__ void advance() {
         asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();
         parity ^= 1;
         rec -= rec_stride;
         remaining--;

@@ -85,7 +85,8 @@ struct ModelConst {
     double AIinv[6][6];                   // (I_b + sum X^T Ia X)^-1
     double bek[5];                        // Bekker soil 5-vector as passed to setParams (BekkerDynamics.cpp:12-21)
     GridTerrain grid;
-    const double* ztab;                   // [kZTabN][kZTabDeg+1] piecewise polynomial of the fixed z-net (build_ztab)
+    const double* exptab;                 // [32] 2^(1 + j/32), j = 0..31 (build_exptab): table of the 8-wide tanh, or nullptr
+    const double* ztab;                   // [kZTabRows][kZTabRow] piecewise polynomials of the fixed z-net and its derivative (build_ztab)
     int terr_kind;                        // used by the TERR_DYN instantiations
     // optional 10-angle contact search (HybridDynamics::get_tire_cpts_sinkages_fancy, HybridDynamics.cpp:258-316), TERR_DYN
     // instantiations only: sin / cos of the candidate pitch angles -0.3 ... +0.3 rad (filled by fill_contact_search)
@@ -163,10 +164,42 @@ AVS_HD double tanh_f64(double x) {
 // W-wide tanh, in place.  Same arithmetic as tanh_f64, but every step is issued for all W elements
 // before the next step starts: with one warp per SM sub-partition the only latency hiding available is
 // instruction-level parallelism, and ptxas does not interleave separately inlined dependent chains.
+#ifndef AVS_TANH_FOLD
+#define AVS_TANH_FOLD 0
+#endif
 template <int W> AVS_HD void tanh_vec(double* x) {
     const double L2E = 1.4426950408889634e+0, MAGIC = 6755399441055744.0;
     const double LN2_HI = 6.93147180559945286e-01, LN2_LO = 2.31904681384629956e-17;
     double a[W], t[W], r[W], p[W];
+#if AVS_TANH_FOLD
+    // -2|x| is never formed: with r' = -r/2 = |x| + k ln2/2 the polynomial of exp(r) = exp(-2 r') has the coefficients
+    // c_n (-2)^n (exact scalings), one FP64 instruction less per element
+#pragma unroll
+    for (int i = 0; i < W; i++) a[i] = fabs(x[i]);
+#pragma unroll
+    for (int i = 0; i < W; i++) t[i] = fma(a[i], -2.0 * L2E, MAGIC);
+#pragma unroll
+    for (int i = 0; i < W; i++) r[i] = t[i] - MAGIC;
+#pragma unroll
+    for (int i = 0; i < W; i++) a[i] = fma(r[i], 0.5 * LN2_HI, a[i]);
+#pragma unroll
+    for (int i = 0; i < W; i++) r[i] = fma(r[i], 0.5 * LN2_LO, a[i]);
+#pragma unroll
+    for (int i = 0; i < W; i++) p[i] = fma(-2048.0 * 2.5110049204818658e-08, r[i], 1024.0 * 2.763265472252779e-07);
+#define AVS_POLY_STEP(C)           \
+    _Pragma("unroll") for (int i = 0; i < W; i++) p[i] = fma(p[i], r[i], C);
+    AVS_POLY_STEP(-512.0 * 2.755724088722987e-06)
+    AVS_POLY_STEP(256.0 * 2.4801485441561313e-05)
+    AVS_POLY_STEP(-128.0 * 0.00019841269890076403)
+    AVS_POLY_STEP(64.0 * 0.0013888888952352863)
+    AVS_POLY_STEP(-32.0 * 0.008333333333319589)
+    AVS_POLY_STEP(16.0 * 0.04166666666648795)
+    AVS_POLY_STEP(-8.0 * 0.1666666666666668)
+    AVS_POLY_STEP(4.0 * 0.5000000000000019)
+    AVS_POLY_STEP(-2.0)
+    AVS_POLY_STEP(1.0)
+#undef AVS_POLY_STEP
+#else
 #pragma unroll
     for (int i = 0; i < W; i++) a[i] = -2.0 * fabs(x[i]);
 #pragma unroll
@@ -192,19 +225,40 @@ template <int W> AVS_HD void tanh_vec(double* x) {
     AVS_POLY_STEP(1.0)
     AVS_POLY_STEP(1.0)
 #undef AVS_POLY_STEP
-    // e = p * 2^k
+#endif
+    // e = p * 2^k  (AVS_TANH_FOLD == 2: 2 e, the exponent patch is k + 1)
 #pragma unroll
     for (int i = 0; i < W; i++) {
 #if defined(__CUDA_ARCH__)
         int k = __double2loint(t[i]);
-        k = max(k, -1000);
+        k = max(k, -1000) + (AVS_TANH_FOLD == 2 ? 1 : 0);
         p[i] = __hiloint2double(__double2hiint(p[i]) + (k << 20), __double2loint(p[i]));
 #else
         int64_t k = (int64_t)(t[i] - MAGIC);
         if (k < -1000) k = -1000;
-        p[i] = ldexp(p[i], (int)k);
+        p[i] = ldexp(p[i], (int)k + (AVS_TANH_FOLD == 2 ? 1 : 0));
 #endif
     }
+#if AVS_TANH_FOLD == 2
+    // 1 - 2e / (1 + e): one FP64 instruction less than (1 - e) / (1 + e), same absolute accuracy
+#pragma unroll
+    for (int i = 0; i < W; i++) a[i] = fma(p[i], 0.5, 1.0);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+    for (int i = 0; i < W; i++) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r[i]) : "d"(a[i]));
+#pragma unroll
+    for (int i = 0; i < W; i++) t[i] = fma(-a[i], r[i], 1.0);
+#pragma unroll
+    for (int i = 0; i < W; i++) t[i] = fma(t[i], t[i], t[i]);
+#pragma unroll
+    for (int i = 0; i < W; i++) r[i] = fma(r[i], t[i], r[i]);
+#else
+#pragma unroll
+    for (int i = 0; i < W; i++) r[i] = 1.0 / a[i];
+#endif
+#pragma unroll
+    for (int i = 0; i < W; i++) t[i] = fma(-p[i], r[i], 1.0);
+#else
     // (1 - e) / (1 + e)
 #pragma unroll
     for (int i = 0; i < W; i++) { a[i] = 1.0 + p[i]; p[i] = 1.0 - p[i]; }
@@ -223,9 +277,90 @@ template <int W> AVS_HD void tanh_vec(double* x) {
 #pragma unroll
     for (int i = 0; i < W; i++) t[i] = p[i] / a[i];
 #endif
+#endif
 #pragma unroll
     for (int i = 0; i < W; i++) x[i] = copysign(t[i], x[i]);
 }
+
+// ---- 8-wide tanh with a 32-entry exponential table (the hot path of the forward sweep) -----------------------------------------
+// tanh|x| = 1 - 2e/(1 + e), e = exp(-2|x|) = 2^k 2^(j/32) exp(r), 32 k + j = round(-2|x| 32/ln2), |r| <= ln2/64, so exp(r) needs
+// degree 6 instead of 11 (truncation 3.5e-18).  Everything is written in r' = -r/2 = |x| + m ln2/64 so that -2|x| is never formed,
+// and the table holds 2 * 2^(j/32) so that 2e falls out of the exponent patch: 16 FP64-pipe instructions + 1 MUFU + one 8-byte
+// table load per element (the table is 256 bytes: two L1 lines) instead of 22.  The 16 tanh per wheel and ODE evaluation are
+// 47 % of the forward kernel's FP64 instructions, and that part of the stage is pipe-bound.
+// Absolute error <= ~3e-16 like tanh_vec (table entries are rounded: 1.1e-16 relative in e).
+template <int W> AVS_HD void tanh_tab_vec(const double* __restrict__ tab, double* x) {
+    const double MAGIC = 6755399441055744.0;
+    const double C = -92.332482616893656768;                                // -64 / ln 2
+    const double L_HI = 6.93147180559945286e-01 / 64.0, L_LO = 2.31904681384629956e-17 / 64.0;  // ln2 / 64, hi + lo
+    double ax[W], t[W], r[W], p[W], e2[W];
+#pragma unroll
+    for (int i = 0; i < W; i++) { const double a = fabs(x[i]); ax[i] = a < 20.0 ? a : 20.0; }   // tanh(20) = 1 - 8e-18
+#pragma unroll
+    for (int i = 0; i < W; i++) t[i] = fma(ax[i], C, MAGIC);                // m = round(-64 |x| / ln2) in the low mantissa bits
+#pragma unroll
+    for (int i = 0; i < W; i++) r[i] = t[i] - MAGIC;
+#pragma unroll
+    for (int i = 0; i < W; i++) ax[i] = fma(r[i], L_HI, ax[i]);
+#pragma unroll
+    for (int i = 0; i < W; i++) r[i] = fma(r[i], L_LO, ax[i]);              // r' = |x| + m ln2/64 in [-ln2/128, ln2/128]; exp(-2 r') follows
+#pragma unroll
+    for (int i = 0; i < W; i++) {
+#if defined(__CUDA_ARCH__)
+        const int m = __double2loint(t[i]);
+        e2[i] = __ldg(tab + (m & 31));
+        e2[i] = __hiloint2double(__double2hiint(e2[i]) + ((m >> 5) << 20), __double2loint(e2[i]));
+#else
+        const int64_t m = (int64_t)(t[i] - MAGIC);
+        e2[i] = ldexp(tab[m & 31], (int)(m >> 5));
+#endif
+    }
+    // exp(-2 r') = 1 + r' q(r'),  q = -2 + 2 r' - 4/3 r'^2 + 2/3 r'^3 - 4/15 r'^4 + 4/45 r'^5
+#pragma unroll
+    for (int i = 0; i < W; i++) p[i] = fma(8.8888888888888892e-02, r[i], -2.6666666666666666e-01);
+#pragma unroll
+    for (int i = 0; i < W; i++) p[i] = fma(p[i], r[i], 6.6666666666666663e-01);
+#pragma unroll
+    for (int i = 0; i < W; i++) p[i] = fma(p[i], r[i], -1.3333333333333333e+00);
+#pragma unroll
+    for (int i = 0; i < W; i++) p[i] = fma(p[i], r[i], 2.0);
+#pragma unroll
+    for (int i = 0; i < W; i++) p[i] = fma(p[i], r[i], -2.0);
+#pragma unroll
+    for (int i = 0; i < W; i++) p[i] = fma(p[i], r[i], 1.0);
+#pragma unroll
+    for (int i = 0; i < W; i++) e2[i] *= p[i];                              // 2 e
+#pragma unroll
+    for (int i = 0; i < W; i++) ax[i] = fma(e2[i], 0.5, 1.0);               // d = 1 + e in [1, 2]
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+    for (int i = 0; i < W; i++) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r[i]) : "d"(ax[i]));
+#pragma unroll
+    for (int i = 0; i < W; i++) t[i] = fma(-ax[i], r[i], 1.0);
+#pragma unroll
+    for (int i = 0; i < W; i++) t[i] = fma(t[i], t[i], t[i]);
+#pragma unroll
+    for (int i = 0; i < W; i++) r[i] = fma(r[i], t[i], r[i]);
+#else
+#pragma unroll
+    for (int i = 0; i < W; i++) r[i] = 1.0 / ax[i];
+#endif
+#pragma unroll
+    for (int i = 0; i < W; i++) t[i] = fma(-e2[i], r[i], 1.0);
+#pragma unroll
+    for (int i = 0; i < W; i++) x[i] = copysign(t[i], x[i]);
+}
+inline void build_exptab(double* tab32) {
+    for (int j = 0; j < 32; j++) tab32[j] = (double)(2.0L * exp2l((long double)j / 32.0L));
+}
+#ifndef AVS_TANH_TAB
+#define AVS_TANH_TAB 0
+#endif
+#if AVS_TANH_TAB
+#define AVS_TANH8(mc, v) tanh_tab_vec<8>((mc).exptab, v)
+#else
+#define AVS_TANH8(mc, v) tanh_vec<8>(v)
+#endif
 
 AVS_HD double rsqrt_f64(double x) {  // for quaternion re-normalisation, x ~ 1
 #if defined(__CUDA_ARCH__)
@@ -331,14 +466,58 @@ template <int TERR> AVS_HD double altitude(const ModelConst& mc, double x, doubl
 // z4 <= 0 and relu gives exactly 0 with zero derivative, as CondExpGt does.
 constexpr int kZTabDeg = 9, kZTabPerUnit = 16, kZTabN = 832;
 constexpr double kZTabSMax = (double)kZTabN / kZTabPerUnit;
+// Row layout (kZTabRow = 10 doubles = five 16-byte pairs, kZTabRows = kZTabN + 1 rows; row kZTabN is the constant tail):
+//   c0..c9 : value polynomial in y = 16 s0 - (i + 1/2), y in [-1/2, 1/2]  (interval i = [i/16, (i+1)/16], centre form)
+// Evaluation is branch-free and short: the interval index comes out of the mantissa of (16 s0 - 1/2) + 2^52 + 2^51 (round to
+// nearest: no F2I / I2F round trip), the coefficients arrive as five 16-byte loads, and the polynomial is evaluated by
+// Estrin's scheme (depth 4 after the loads instead of 9 dependent Horner steps).  The first version sat in a divergent region
+// (s0 > 0 ? ... : 0) that ptxas could not interleave with the xy-net: ~300 cycles of serial chain per ODE stage on the single
+// resident warp (ncu source page, round 2).  Forward-only rollouts use this form (28.6 -> 28.0 ms at 4096 x 600 rows); the
+// instantiation that also stores the adjoint's records keeps the joint value + derivative Horner pass (ztab_eval_d).
+constexpr int kZTabRow = kZTabDeg + 1, kZTabRows = kZTabN + 1;
 
-AVS_HD double ztab_eval(const double* tab, double s0, double* dz /* d z4 / d s0, or nullptr */) {
+struct ZTabPos { double y; const double* row; };
+AVS_HD ZTabPos ztab_pos(const double* tab, double s0) {
+    const double MAGIC = 6755399441055744.0;
+    double sc = s0 > 0.0 ? s0 : 0.0;
+    sc = sc < kZTabSMax ? sc : kZTabSMax;
+    const double v = fma(sc, (double)kZTabPerUnit, -0.5);   // in [-1/2, kZTabN - 1/2]
+    const double t = v + MAGIC;                             // nearest integer i in [0, kZTabN] in the low mantissa bits
+#if defined(__CUDA_ARCH__)
+    const int i = __double2loint(t);
+#else
+    const int i = (int)(int64_t)(t - MAGIC);
+#endif
+    return ZTabPos{v - (t - MAGIC), tab + (size_t)i * kZTabRow};
+}
+struct ZPair { double x, y; };
+AVS_HD ZPair ztab_ld(const double* row, int i) {
+#if defined(__CUDA_ARCH__)
+    const double2 v = __ldg(reinterpret_cast<const double2*>(row) + i);
+    return ZPair{v.x, v.y};
+#else
+    return ZPair{row[2 * i], row[2 * i + 1]};
+#endif
+}
+// z4(max(s0, 0)); callers apply the relu gate themselves
+AVS_HD double ztab_eval(const double* tab, double s0) {
+    const ZTabPos q = ztab_pos(tab, s0);
+    const ZPair c01 = ztab_ld(q.row, 0), c23 = ztab_ld(q.row, 1), c45 = ztab_ld(q.row, 2), c67 = ztab_ld(q.row, 3), c89 = ztab_ld(q.row, 4);
+    const double y = q.y, y2 = y * y, y4 = y2 * y2, y8 = y4 * y4;
+    const double a0 = fma(c01.y, y, c01.x), a1 = fma(c23.y, y, c23.x), a2 = fma(c45.y, y, c45.x), a3 = fma(c67.y, y, c67.x), a4 = fma(c89.y, y, c89.x);
+    const double b0 = fma(a1, y2, a0), b1 = fma(a3, y2, a2);
+    return fma(a4, y8, fma(b1, y4, b0));
+}
+// value AND derivative (d z4 / d s0) for s0 > 0, by one joint Horner pass over the value coefficients — the form the STORE
+// instantiation of the forward kernel keeps: it runs at its register cap, and there the short dependent chain with ten 8-byte
+// coefficient loads schedules better than Estrin's scheme with 16-byte loads (measured, round 2: 11.08 against 11.3-11.9 ms)
+AVS_HD double ztab_eval_d(const double* tab, double s0, double& dz) {
     const double sc = s0 < kZTabSMax ? s0 : kZTabSMax;
     const double u = sc * (double)kZTabPerUnit;
     int i = (int)u;
     i = i > kZTabN - 1 ? kZTabN - 1 : i;
-    const double x = fma(u - (double)i, 2.0, -1.0);
-    const double* c = tab + (size_t)i * (kZTabDeg + 1);
+    const double y = (u - (double)i) - 0.5;
+    const double* c = tab + (size_t)i * kZTabRow;
     double cc[kZTabDeg + 1];
 #pragma unroll
     for (int k = 0; k <= kZTabDeg; k++) {
@@ -349,18 +528,13 @@ AVS_HD double ztab_eval(const double* tab, double s0, double* dz /* d z4 / d s0,
 #endif
     }
     double p = cc[kZTabDeg], d = 0.0;
-    if (dz) {
 #pragma unroll
-        for (int k = kZTabDeg - 1; k >= 0; k--) { d = fma(d, x, p); p = fma(p, x, cc[k]); }
-        *dz = s0 < kZTabSMax ? d * (2.0 * kZTabPerUnit) : 0.0;
-    } else {
-#pragma unroll
-        for (int k = kZTabDeg - 1; k >= 0; k--) p = fma(p, x, cc[k]);
-    }
+    for (int k = kZTabDeg - 1; k >= 0; k--) { d = fma(d, y, p); p = fma(p, y, cc[k]); }
+    dz = s0 < kZTabSMax ? d * (double)kZTabPerUnit : 0.0;
     return p;
 }
 
-// host-side construction (long double): Chebyshev-node interpolation per interval, converted to monomials in x in [-1,1]
+// host-side construction (long double): Chebyshev-node interpolation per interval, converted to monomials in y in [-1/2, 1/2]
 inline void build_ztab(const double Z0[8], const double Z2[8][8], const double Z4[8], double* tab) {
     const int n = kZTabDeg + 1;
     const long double PI = 3.14159265358979323846264338327950288L;
@@ -370,30 +544,35 @@ inline void build_ztab(const double Z0[8], const double Z2[8][8], const double Z
     Tm[1][1] = 1;
     for (int k = 2; k < n; k++)
         for (int j = 0; j < n; j++) Tm[k][j] = (j > 0 ? 2 * Tm[k - 1][j - 1] : 0) - Tm[k - 2][j];
+    auto znet = [&](long double sv) {
+        long double g0[8], z = 0;
+        for (int j = 0; j < 8; j++) g0[j] = tanhl((long double)Z0[j] * sv);
+        for (int j = 0; j < 8; j++) {
+            long double acc = 0;
+            for (int q = 0; q < 8; q++) acc += (long double)Z2[j][q] * g0[q];
+            z += (long double)Z4[j] * tanhl(acc);
+        }
+        return z;
+    };
     for (int i = 0; i < kZTabN; i++) {
         const long double a = (long double)i / kZTabPerUnit, b = (long double)(i + 1) / kZTabPerUnit;
-        long double fx[kZTabDeg + 1], xs[kZTabDeg + 1];
-        for (int k = 0; k < n; k++) {
-            xs[k] = cosl(PI * (2 * k + 1) / (2 * n));
-            const long double sv = (a + b) / 2 + (b - a) / 2 * xs[k];
-            long double g0[8], z = 0;
-            for (int j = 0; j < 8; j++) g0[j] = tanhl((long double)Z0[j] * sv);
-            for (int j = 0; j < 8; j++) {
-                long double acc = 0;
-                for (int q = 0; q < 8; q++) acc += (long double)Z2[j][q] * g0[q];
-                z += (long double)Z4[j] * tanhl(acc);
-            }
-            fx[k] = z;
-        }
-        long double mono[kZTabDeg + 1] = {0};
+        long double fx[kZTabDeg + 1];
+        for (int k = 0; k < n; k++) fx[k] = znet((a + b) / 2 + (b - a) / 2 * cosl(PI * (2 * k + 1) / (2 * n)));
+        long double mono[kZTabDeg + 1] = {0};  // in x = 2 y in [-1, 1]
         for (int m = 0; m < n; m++) {  // Chebyshev coefficient a_m
             long double am = 0;
             for (int k = 0; k < n; k++) am += fx[k] * cosl(PI * m * (2 * k + 1) / (2 * n));
             am *= (m == 0 ? 1.0L : 2.0L) / n;
             for (int j = 0; j < n; j++) mono[j] += am * Tm[m][j];
         }
-        for (int j = 0; j < n; j++) tab[(size_t)i * n + j] = (double)mono[j];
+        double* row = tab + (size_t)i * kZTabRow;
+        long double scale = 1;  // x^j = 2^j y^j
+        for (int j = 0; j < n; j++) { mono[j] *= scale; scale *= 2; row[j] = (double)mono[j]; }
     }
+    // tail row: s0 >= kZTabSMax (every first-layer unit saturated): constant value, zero derivative
+    double* last = tab + (size_t)kZTabN * kZTabRow;
+    for (int j = 0; j < kZTabRow; j++) last[j] = 0.0;
+    last[0] = (double)znet((long double)kZTabSMax);
 }
 
 struct NNAct {
@@ -404,17 +583,21 @@ struct NNAct {
 
 // in: contact velocity (vx, vy), wheel speed w, sinkage zr -> (Fx, Fy, Fz) before the damping term.
 // Loop nests are ordered so that consecutive instructions belong to different accumulators (ILP).
-// in: contact velocity (vx, vy), wheel speed w, sinkage zr -> (Fx, Fy, Fz) before the damping term.
-// Loop nests are ordered so that consecutive instructions belong to different accumulators (ILP).
 template <bool WANT_D = false>
 AVS_HD void tire_nn_fwd(const ModelConst& mc, double vx, double vy, double w, double zr, double F[3], NNAct& a) {
     const double s0 = zr * (1.0 / kInStd0);
     a.s1 = (w * kTireRadius - vx) * (1.0 / kInStd1);
     a.s2 = w * (1.0 / kInStd2);
     a.s3 = vy * (1.0 / kInStd3);
-    // z-branch (table); issued first so that its loads overlap the xy-net
+    // z-branch (table); for s0 <= 0 relu gives exactly 0 with zero derivative, as CondExpGt does
     a.dz4 = 0.0;
-    const double z4 = s0 > 0.0 ? ztab_eval(mc.ztab, s0, WANT_D ? &a.dz4 : nullptr) : 0.0;
+    double z4;
+    if (WANT_D) {
+        z4 = s0 > 0.0 ? ztab_eval_d(mc.ztab, s0, a.dz4) : 0.0;
+    } else {
+        const double zt = ztab_eval(mc.ztab, s0);  // branch-free: evaluated at max(s0, 0)
+        z4 = s0 > 0.0 ? zt : 0.0;
+    }
     a.z4 = z4;
 #pragma unroll
     for (int j = 0; j < 8; j++) a.h0[j] = mc.W0[j][0] * a.s1;
@@ -422,7 +605,7 @@ AVS_HD void tire_nn_fwd(const ModelConst& mc, double vx, double vy, double w, do
     for (int j = 0; j < 8; j++) a.h0[j] = fma(mc.W0[j][1], a.s2, a.h0[j]);
 #pragma unroll
     for (int j = 0; j < 8; j++) a.h0[j] = fma(mc.W0[j][2], a.s3, a.h0[j]);
-    tanh_vec<8>(a.h0);
+    AVS_TANH8(mc, a.h0);
 #pragma unroll
     for (int j = 0; j < 8; j++) a.h2[j] = mc.W2[j][0] * a.h0[0];
 #pragma unroll
@@ -430,7 +613,7 @@ AVS_HD void tire_nn_fwd(const ModelConst& mc, double vx, double vy, double w, do
 #pragma unroll
         for (int j = 0; j < 8; j++) a.h2[j] = fma(mc.W2[j][k], a.h0[k], a.h2[j]);
     }
-    tanh_vec<8>(a.h2);
+    AVS_TANH8(mc, a.h2);
     // two output rows, each as two interleaved partial sums
     double f0a = mc.W4[0][0] * a.h2[0], f0b = mc.W4[0][1] * a.h2[1];
     double f1a = mc.W4[1][0] * a.h2[0], f1b = mc.W4[1][1] * a.h2[1];

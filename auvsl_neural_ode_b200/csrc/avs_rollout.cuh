@@ -11,9 +11,12 @@
 //   ctrl    [T-1][2][N]      (vl, vr) applied during macro step i -> i+1 (= traj[i].vl/vr, Trainer.cpp:564-565)
 //   x_list  [T][23][N]       optional: the reference's x_list (row 0 = x0 + controls of row 0)
 //   x_final [21][N]          optional
-//   ckpt    [S*4+1][Nc][14]  one record per RK4 stage (S = (T-1)*substeps steps) + one for the final state:
-//                            13 state entries + the inverse quaternion norm the reverse sweep needs with it.
-//                            This stream replaces the tape (448 B per vehicle-step)
+//   ckpt    [S*4+1][tiles][7][8][2]  one record per RK4 stage (S = (T-1)*substeps steps) + one for the final state:
+//                            13 state entries + the inverse quaternion norm the reverse sweep needs with it, as seven
+//                            16-byte pairs.  The records of the 8 vehicles of a warp form one 896-byte "state tile",
+//                            pair-major (pair r of vehicle v at r*16 + v*2 doubles): the forward warp's eight writer
+//                            lanes store one full 128-byte line per pair, the reverse warp fetches the tile with two
+//                            contiguous cp.async.  This stream replaces the tape (448 B per vehicle-step)
 //   act     [S*4][4*Nc][20]  per-wheel tire-network activation records of every stage (2560 B per vehicle-step):
 //                            the reverse sweep reads them instead of re-evaluating tanh / terrain
 //   gt      [T][3][N]        (yaw, x, y) ground truth rows
@@ -66,11 +69,17 @@ AVS_HD double ld(const double* p) {
 }
 
 constexpr int kCkRows = 14;  // 13 live states + 1 inverse norm per stage record
+// state tiles: the records of 8 consecutive vehicles (one warp of either rollout kernel), pair-major
+constexpr int kCkTileVeh = 8, kCkPairStride = 2 * kCkTileVeh, kCkTile = kCkRows * kCkTileVeh;  // 16 / 112 doubles
+AVS_HD size_t ck_rec_stride(size_t nc) { return ((nc + kCkTileVeh - 1) / kCkTileVeh) * kCkTile; }  // doubles between consecutive records
+AVS_HD size_t ck_lane_offset(size_t n) { return (n / kCkTileVeh) * kCkTile + (n % kCkTileVeh) * 2; }  // pair 0 of vehicle n inside a record
+// element c of the record whose pair 0 is at p
+AVS_HD size_t ck_elem(int c) { return (size_t)(c >> 1) * kCkPairStride + (c & 1); }
 
 // writes stage records straight to HBM as seven 16-byte pairs (only the writer lane of a group stores)
 struct CkptSink {
-    double* base;  // &ckpt[step*4][n][0]
-    size_t rec_stride;  // doubles between consecutive records = Nc * kCkRows
+    double* base;  // pair 0 of vehicle n in record step*4
+    size_t rec_stride;  // doubles between consecutive records = ck_rec_stride(Nc)
     bool on;
     template <class V> AVS_HD void stage(int s, const V& T, double inv) {
         if (!on) return;
@@ -79,18 +88,18 @@ struct CkptSink {
     template <class V> AVS_HD static void ckpt_store(double* p, const V& T, double inv) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
-        for (int i = 0; i < 6; i++) reinterpret_cast<double2*>(p)[i] = make_double2(T[2 * i], T[2 * i + 1]);
-        reinterpret_cast<double2*>(p)[6] = make_double2(T[12], inv);
+        for (int i = 0; i < 6; i++) *reinterpret_cast<double2*>(p + (size_t)i * kCkPairStride) = make_double2(T[2 * i], T[2 * i + 1]);
+        *reinterpret_cast<double2*>(p + (size_t)6 * kCkPairStride) = make_double2(T[12], inv);
 #else
-        for (int c = 0; c < 13; c++) p[c] = T[c];
-        p[13] = inv;
+        for (int c = 0; c < 13; c++) p[ck_elem(c)] = T[c];
+        p[ck_elem(13)] = inv;
 #endif
     }
 };
 
 // reverse record stream on the host / generic path: plain loads, no prefetch
 template <class St> struct CkptStreamSimple {
-    const double* rec;  // current record in HBM
+    const double* rec;  // current record in HBM (pair 0 of this vehicle)
     size_t rec_stride;  // doubles between consecutive records
     St buf;             // 14-slot scratch column
     const double* actp; // activation records of the current record's stage (lane-offset applied)
@@ -98,7 +107,7 @@ template <class St> struct CkptStreamSimple {
     AVS_HD const double* act() const { return actp; }
     AVS_HD void load() {
 #pragma unroll
-        for (int c = 0; c < kCkRows; c++) buf[c] = ld(rec + c);
+        for (int c = 0; c < kCkRows; c++) buf[c] = ld(rec + ck_elem(c));
     }
     AVS_HD St cur() const { return buf; }
     AVS_HD void advance() { rec -= rec_stride; actp -= act_stride; load(); }
@@ -123,7 +132,7 @@ template <bool STORE, class Ode, class St> struct GenericStep {
         St X = S, ACC = S.sub(13), TT = S.sub(26), KK = S.sub(39);
         if (STORE) {
             ode.act_step = a.act + ((step * 4) * (4 * NK) + (size_t)4 * n + lane0) * kActLen;
-            CkptSink sink{a.ckpt + ((step * 4) * NK + n) * kCkRows, NK * kCkRows, writer};
+            CkptSink sink{a.ckpt + (step * 4) * ck_rec_stride(NK) + ck_lane_offset(n), ck_rec_stride(NK), writer};
             rk4_fwd(ode, X, ACC, TT, KK, sink, inv_carry);
         } else {
             NullSink sink;
@@ -170,8 +179,8 @@ AVS_HD void rollout_fwd_body(const RolloutArgs& a, int n, int lane0, bool valid,
         }
     }
     if (STORE && writer) {
-        double* last = a.ckpt + (((size_t)(a.T - 1) * a.substeps * 4) * NK + n) * kCkRows;
-        AVS_DBG_RANGE("final state record (store)", last, kCkRows, a.ckpt, a.ckpt_doubles);
+        double* last = a.ckpt + ((size_t)(a.T - 1) * a.substeps * 4) * ck_rec_stride(NK) + ck_lane_offset(n);
+        AVS_DBG_RANGE("final state record (store)", last, 6 * kCkPairStride + 2, a.ckpt, a.ckpt_doubles);
         CkptSink::ckpt_store(last, X, inv_carry);
     }
     if (a.x_final && writer) {
@@ -187,7 +196,7 @@ AVS_HD void rollout_fwd_body(const RolloutArgs& a, int n, int lane0, bool valid,
     }
 }
 
-constexpr int kBwdScratch = 87;  // LAM[13] | YB[13] | KB[13] | record buffer A[14] | record buffer B[14] | activation record[20]
+constexpr int kBwdScratch = 87;  // host harness: LAM[13] | YB[13] | KB[13] | record buffer[14] | ...
 
 // Reverse sweep over the checkpoints written by rollout_fwd_body<.., STORE=true>.
 //   L = (sum_{i=1}^{T-1} l_i) / T / traj_len   (Trainer.cpp:612-649)

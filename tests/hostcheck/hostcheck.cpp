@@ -39,7 +39,10 @@ static void fill_mc(ModelConst& mc, const double* p416, const double* zw152, con
     fill_contact_search(mc);
     mc.terr_kind = 0;
     static std::vector<double> ztab;
-    if (zw152) { ztab.resize((size_t)kZTabN * (kZTabDeg + 1)); build_ztab(mc.Z0, mc.Z2, mc.Z4, ztab.data()); mc.ztab = ztab.data(); }
+    if (zw152) { ztab.resize((size_t)kZTabRows * kZTabRow); build_ztab(mc.Z0, mc.Z2, mc.Z4, ztab.data()); mc.ztab = ztab.data(); }
+    static double etab[32];
+    build_exptab(etab);
+    mc.exptab = etab;
     mc.grid.height = height; mc.grid.soil = soil; mc.grid.nx = nx; mc.grid.ny = ny;
     mc.grid.x0 = x0; mc.grid.y0 = y0; mc.grid.inv_dx = 1.0 / dx; mc.grid.inv_dy = 1.0 / dy;
 }
@@ -112,7 +115,7 @@ template <int TERR> static void bwd_body(const ModelConst& mc, const RolloutArgs
     double sc[kBwdScratch];
     auto mk = [&mc, &acc](double ul, double ur) { return OdeBwdInline<4, TERR, HostAcc>{mc, 0, ul, ur, acc}; };
     const size_t nrec = (size_t)(a.T - 1) * a.substeps * 4;
-    CkptStreamSimple<Scratch<1>> st{a.ckpt + (nrec * a.Nc + n) * kCkRows, (size_t)a.Nc * kCkRows, Scratch<1>{sc + 52},
+    CkptStreamSimple<Scratch<1>> st{a.ckpt + nrec * ck_rec_stride(a.Nc) + ck_lane_offset(n), ck_rec_stride(a.Nc), Scratch<1>{sc + 52},
                                     a.act + (nrec * 4 * a.Nc + (size_t)4 * n) * kActLen, (size_t)4 * a.Nc * kActLen};
     st.load();
     rollout_bwd_body(a, n, loss, Scratch<1>{sc}, st, mk);
@@ -149,10 +152,24 @@ void hc_zweights(double* out152) { memcpy(out152, kFixedZ0, 64); memcpy(out152 +
 void hc_default_params(double* p416) { for (int k = 0; k < 4; k++) { memcpy(p416 + 104 * k, kDefaultW0, 192); memcpy(p416 + 104 * k + 24, kDefaultW2, 512); memcpy(p416 + 104 * k + 88, kDefaultW4, 128); } }
 void hc_aiinv(double* out36) { double A[6][6]; compute_AIinv(A); memcpy(out36, A, sizeof(A)); }
 double hc_tanh(double x) { return tanh_f64(x); }
+double hc_tanh_tab(double x) {
+    double tab[32], v[1] = {x};
+    build_exptab(tab);
+    tanh_tab_vec<1>(tab, v);
+    return v[0];
+}
 double hc_ztab(double s0, double* dz) {
     static std::vector<double> t;
-    if (t.empty()) { t.resize((size_t)kZTabN * (kZTabDeg + 1)); build_ztab((const double*)kFixedZ0, (const double(*)[8])kFixedZ2, (const double*)kFixedZ4, t.data()); }
-    return ztab_eval(t.data(), s0, dz);
+    if (t.empty()) { t.resize((size_t)kZTabRows * kZTabRow); build_ztab((const double*)kFixedZ0, (const double(*)[8])kFixedZ2, (const double*)kFixedZ4, t.data()); }
+    // both evaluators of the table: the branch-free value form and the joint value + derivative Horner pass
+    const double v = ztab_eval(t.data(), s0);
+    if (dz) {
+        double d = 0.0;
+        const double v2 = s0 > 0.0 ? ztab_eval_d(t.data(), s0, d) : v;
+        *dz = d;
+        if (fabs(v2 - v) > 4e-16 * (1.0 + fabs(v))) return NAN;  // the two forms must agree to rounding
+    }
+    return v;
 }
 
 void hc_bekker_tire(const hc_model* m, double cvx, double cvy, double w, double sinkage, double* F3) {
@@ -225,7 +242,7 @@ void hc_rollout_margins(const hc_model* m, int N, int T, int substeps, const dou
 }
 void hc_rollout_grad(const hc_model* m, int N, int T, int substeps, const double* x0, const double* ctrl, const double* gt, double* loss, double* gps104xN) {
     ModelConst mc; mk(m, mc);
-    std::vector<double> ckpt(((size_t)(T - 1) * substeps * 4 + 1) * kCkRows * N);
+    std::vector<double> ckpt(((size_t)(T - 1) * substeps * 4 + 1) * ck_rec_stride(N));
     RolloutArgs a; memset(&a, 0, sizeof(a));
     std::vector<double> actbuf((size_t)(T - 1) * substeps * 4 * kActLen * 4 * N);
     a.N = N; a.Nc = N; a.T = T; a.substeps = substeps; a.x0 = x0; a.ctrl = ctrl; a.ckpt = ckpt.data(); a.act = actbuf.data(); a.gt = gt;

@@ -25,6 +25,10 @@ def lib():
         _lib = C.CDLL(_SO)
         _lib.hc_tanh.restype = C.c_double
         _lib.hc_tanh.argtypes = [C.c_double]
+        _lib.hc_tanh_tab.restype = C.c_double
+        _lib.hc_tanh_tab.argtypes = [C.c_double]
+        _lib.hc_ztab.restype = C.c_double
+        _lib.hc_ztab.argtypes = [C.c_double, C.c_void_p]
     return _lib
 
 
@@ -45,6 +49,13 @@ def zweights():
     z = np.zeros(152)
     lib().hc_zweights(_p(z))
     return z
+
+
+def ztab(s0):
+    """(z4, d z4 / d s0) of the fixed z-network from the device's piecewise-polynomial table (ztab_eval, avs_model.cuh)"""
+    d = np.zeros(1)
+    v = lib().hc_ztab(float(s0), _p(d))
+    return v, float(d[0])
 
 
 def default_params():

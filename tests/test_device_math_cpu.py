@@ -28,6 +28,31 @@ def test_tanh_accuracy():
     assert err <= 4.5e-16
 
 
+def test_ztable_matches_fixed_z_network():
+    """the constant-folded z-branch (piecewise degree-9 table, Estrin evaluation, stored derivative polynomial) against the
+    network it replaces (TireNetwork.cpp:17-32, 60-71) evaluated in extended precision: value and derivative"""
+    zw = hc.zweights().astype(np.longdouble)
+    Z0, Z2, Z4 = zw[:8], zw[8:72].reshape(8, 8), zw[72:80]
+
+    def znet(s):
+        g0 = np.tanh(Z0 * s)
+        g2 = np.tanh(Z2 @ g0)
+        dz = Z4 @ ((1 - g2 * g2) * (Z2 @ ((1 - g0 * g0) * Z0)))
+        return Z4 @ g2, dz
+
+    rng = np.random.default_rng(5)
+    ss = np.concatenate([rng.uniform(0, 2, 3000), rng.uniform(0, 52, 2000), np.arange(0, 833) / 16.0, np.arange(0, 833) / 16.0 + 1e-13,
+                         [1e-300, 1e-9, 51.99999, 52.0, 52.5, 1e3]])
+    scale = max(abs(float(znet(np.longdouble(s))[0])) for s in (0.5, 5.0, 52.0))
+    ev = ed = 0.0
+    for s in ss:
+        v, d = hc.ztab(s)
+        rv, rd = znet(np.longdouble(s))
+        ev = max(ev, abs(v - float(rv)) / scale)
+        ed = max(ed, abs(d - float(rd)) / scale)
+    assert ev < 4e-16 and ed < 2e-13, (ev, ed)
+
+
 def test_aiinv_is_inverse_of_assembled_inertia():
     # SURVEY.md Appendix A3 tripwires for AI_b
     A = np.linalg.inv(hc.aiinv())
