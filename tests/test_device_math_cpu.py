@@ -49,7 +49,8 @@ def test_ztable_matches_fixed_z_network():
         v, d = hc.ztab(s)
         rv, rd = znet(np.longdouble(s))
         ev = max(ev, abs(v - float(rv)) / scale)
-        ed = max(ed, abs(d - float(rd)) / scale)
+        if s > 0.0:  # at s0 <= 0 the relu gate is closed: value 0, derivative 0 (CondExpGt)
+            ed = max(ed, abs(d - float(rd)) / scale)
     assert ev < 4e-16 and ed < 2e-13, (ev, ed)
 
 
