@@ -28,9 +28,9 @@ constexpr int kBwdThreads = 2 * kBwdBlock;  // producer warp + consumer warp
 // (3x3 worth of FMAs instead of the layered back-propagation, 5 staged values instead of 37, no activation traffic), the
 // consumer owns the activation stream (own cp.async ring, three tiles deep), forms J, runs the layered back-propagation for
 // the weight gradient and accumulates the outer products.
-// scratch columns (16-byte pairs, 14 slots per 13-vector): LAM 0 | YB 14 | KB 28 | state tile A 42 | state tile B 46
-// (kCkTile = 112 doubles = 3.5 columns each) | activation tiles 50 (3 x kActLen) | J ring | F ring | dW4
-constexpr int kB2SlotRecA = 42, kB2SlotRecB = 46, kB2SlotT = 50, kB2SlotJ = kB2SlotT + 3 * kActLen, kB2SlotF = kB2SlotJ + 2 * kJLen, kB2SlotG4 = kB2SlotF + 2 * kFLen, kB2Slots = kB2SlotG4 + 16;  // + dW4 accumulators (16 per lane, as 8 pairs)
+// shared memory, in columns of kBwdBlock doubles: adjoint tiles LAM | YB | KB (3 x kCkTile doubles) 0 | state tile A 11 |
+// state tile B 15 | activation tiles 19 (3 x kActLen columns) | J ring | F ring | dW4
+constexpr int kB2SlotRecA = 11, kB2SlotRecB = 15, kB2SlotT = 19, kB2SlotJ = kB2SlotT + 3 * kActLen, kB2SlotF = kB2SlotJ + 2 * kJLen, kB2SlotG4 = kB2SlotF + 2 * kFLen, kB2Slots = kB2SlotG4 + 16;  // + dW4 accumulators (16 per lane, as 8 pairs)
 
 template <int TERR>
 __global__ void __launch_bounds__(kBwdThreads) rollout_bwd2_kernel(const __grid_constant__ RolloutArgs a) {
@@ -67,7 +67,8 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd2_kernel(const __grid_
         const size_t rstride = ck_rec_stride(a.Nc);
         CkptStreamRec<kBwdBlock> st{a.ckpt + (size_t)nrec * rstride + (size_t)blockIdx.x * kCkTile, rstride, nrec, kB2SlotRecA, kB2SlotRecB, 0, voff, a.ckpt, a.ckpt_doubles};
         st.init();
-        rollout_bwd_body(a, n, loss, pair_col<kBwdBlock>(0), st, mk_odeb);
+        static_assert(3 * kCkTile <= kB2SlotRecA * kBwdBlock && kB2SlotRecA * kBwdBlock + kCkTile <= kB2SlotRecB * kBwdBlock && kB2SlotRecB * kBwdBlock + kCkTile <= kB2SlotT * kBwdBlock, "tile map");
+        rollout_bwd_body(a, n, loss, rec_col<kBwdBlock>(0, voff), st, mk_odeb);
         if (writer) a.loss[n] = loss;
     } else {
         // ---------------- consumer warp: activation stream, Jacobians one stage ahead, weight gradient
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd2_kernel(const __grid_
         };
         prefetch(0, 0);
         prefetch(1, 1);
-        asm volatile("cp.async.wait_all;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         publish_jac(0, 0);
         int t0 = 0, t1 = 1, t2 = 2;  // tiles of reverse stages j, j+1, j+2
 #pragma unroll 1
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd2_kernel(const __grid_
                     g[kOffW0 + k * 3 + 2] = fma(d0[k], s3, g[kOffW0 + k * 3 + 2]);
                 }
             }
-            asm volatile("cp.async.wait_all;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
             const int tt = t0; t0 = t1; t1 = t2; t2 = tt;
         }
 #pragma unroll

@@ -213,9 +213,12 @@ typedef PairCol<kCkTileVeh> RecCol;
 template <int BLOCK> __device__ __forceinline__ RecCol rec_col(int slot, int voff /* 2 * (vehicle % 8) */) { return RecCol{g_smem + (size_t)slot * BLOCK + voff}; }
 template <int TERR, int BLOCK>
 __device__ __noinline__ void ode_bwd_call2(int lane0, int voff, int slotXS, int slotLAM, int slotJ, int slotF, double ul, double ur, int stage_count, int s) {
-    // all loop-carried vectors are 16-byte pairs (LDS.128 / STS.128): LAM | YB | KB, 14 slots each; XS = the staged state tile
+    // XS = the staged state tile; the loop-carried adjoints LAM | YB | KB are vehicle-level 13-vectors, bit-identical in the four
+    // lanes of a vehicle (the butterfly sums are commutative), so they live in three tiles of the same shape: the four lanes
+    // store the same 16 bytes to the same address and read them back by broadcast — one shared-memory wavefront per
+    // LDS.128 / STS.128 of the warp instead of four, and a four times shorter store drain before the callee returns
     const RecCol XS = rec_col<BLOCK>(slotXS, voff);
-    const PairCol<BLOCK> LAM = pair_col<BLOCK>(slotLAM), YB = pair_col<BLOCK>(slotLAM + 14), KB = pair_col<BLOCK>(slotLAM + 28);
+    const RecCol LAM = rec_col<BLOCK>(slotLAM, voff), YB = LAM.sub(13), KB = LAM.sub(26);
     JInSmem<BLOCK> jin{g_smem + (size_t)slotJ * BLOCK + (size_t)threadIdx.x * 2, stage_count};
     FOutSmem<BLOCK> fout{g_smem + (size_t)slotF * BLOCK + threadIdx.x, stage_count};
     double X[14], kb[14], Xb[14];
@@ -287,7 +290,7 @@ template <int BLOCK> struct CkptStreamRec {
         prefetch_prev();
     }
     __device__ __forceinline__ void advance() {
-        asm volatile("cp.async.wait_all;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
         parity ^= 1;
         rec -= rec_stride;
