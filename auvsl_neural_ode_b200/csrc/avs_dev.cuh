@@ -211,8 +211,12 @@ template <int BLOCK> struct FOutSmem {
 // lanes of a vehicle read the same 16 bytes (broadcast), a warp's LDS.128 touches one 128-byte line
 typedef PairCol<kCkTileVeh> RecCol;
 template <int BLOCK> __device__ __forceinline__ RecCol rec_col(int slot, int voff /* 2 * (vehicle % 8) */) { return RecCol{g_smem + (size_t)slot * BLOCK + voff}; }
+// Inlined into the producer's stage loop (round 2): unlike the forward stage — which, inlined into its rolled loop, is
+// re-serialised by ptxas and runs 1.9x slower (28.1 -> 52.1 ms, re-measured) — the adjoint stage loses nothing, and the call
+// cost goes away: ~40-cycle instruction-fetch misses at the call and at the return, the S2R / CgaCtaId address prologue, and
+// the drain of the last STS.128 before RET (11.31 -> 10.91 ms).
 template <int TERR, int BLOCK>
-__device__ __noinline__ void ode_bwd_call2(int lane0, int voff, int slotXS, int slotLAM, int slotJ, int slotF, double ul, double ur, int stage_count, int s) {
+__device__ __forceinline__ void ode_bwd_call2(int lane0, int voff, int slotXS, int slotLAM, int slotJ, int slotF, double ul, double ur, int stage_count, int s) {
     // XS = the staged state tile; the loop-carried adjoints LAM | YB | KB are vehicle-level 13-vectors, bit-identical in the four
     // lanes of a vehicle (the butterfly sums are commutative), so they live in three tiles of the same shape: the four lanes
     // store the same 16 bytes to the same address and read them back by broadcast — one shared-memory wavefront per
