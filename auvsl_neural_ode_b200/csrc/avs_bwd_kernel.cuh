@@ -19,9 +19,6 @@
 namespace avs {
 
 constexpr int kBwdThreads = 2 * kBwdBlock;  // producer warp + consumer warp
-#ifndef AVS_BWD_STAGGER
-#define AVS_BWD_STAGGER 0
-#endif
 
 // ---- split tire adjoint ------------------------------------------------------------------------------------------------
 // Same two roles, different cut: the producer's state chain uses the xy-net Jacobian the consumer formed a stage ahead
@@ -42,19 +39,6 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd2_kernel(const __grid_
     if (!valid) n = a.Nc - 1;
     const bool writer = valid && lane0 == 0;
     const long nrec = (long)(a.T - 1) * a.substeps * 4;
-#if AVS_BWD_STAGGER > 0
-    {   // CTAs in hardware warp slots 4..7 share their two schedulers with the CTAs in slots 0..3 (measured: slot % 4 = scheduler,
-        // a 2-warp CTA takes two consecutive slots).  All CTAs run the same stage loop in near lock-step, so the FP64-dense and the
-        // latency-bound phases of the two warps on a scheduler coincide; starting the second pair part of a stage later
-        // de-correlates them.
-        unsigned wid;
-        asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
-        if (wid & 4u) {
-            const long long t0 = clock64();
-            while (clock64() - t0 < AVS_BWD_STAGGER) {}
-        }
-    }
-#endif
     if (threadIdx.x < kBwdBlock) {
         // ---------------- producer warp: state adjoint
         double loss;
