@@ -26,8 +26,8 @@ constexpr int kBwdThreads = 2 * kBwdBlock;  // producer warp + consumer warp
 // consumer owns the activation stream (own cp.async ring, three tiles deep), forms J, runs the layered back-propagation for
 // the weight gradient and accumulates the outer products.
 // shared memory, in columns of kBwdBlock doubles: adjoint tiles LAM | YB | KB (3 x kCkTile doubles) 0 | state tile A 11 |
-// state tile B 15 | activation tiles 19 (3 x kActLen columns) | J ring | F ring | dW4
-constexpr int kB2SlotRecA = 11, kB2SlotRecB = 15, kB2SlotT = 19, kB2SlotJ = kB2SlotT + 3 * kActLen, kB2SlotF = kB2SlotJ + 2 * kJLen, kB2SlotG4 = kB2SlotF + 2 * kFLen, kB2Slots = kB2SlotG4 + 16;  // + dW4 accumulators (16 per lane, as 8 pairs)
+// state tile B 15 | activation tiles 19 (kTiles x kActLen columns) | J ring | F ring | dW4
+constexpr int kB2SlotRecA = 11, kB2SlotRecB = 15, kB2SlotT = 19, kLook = kRing - 2, kTiles = kRing, kB2SlotJ = kB2SlotT + kTiles * kActLen, kB2SlotF = kB2SlotJ + kRing * kJLen, kB2SlotG4 = kB2SlotF + kRing * kFLen, kB2Slots = kB2SlotG4 + 16;  // + dW4 accumulators (16 per lane, as 8 pairs)
 
 template <int TERR>
 __global__ void __launch_bounds__(kBwdThreads) rollout_bwd2_kernel(const __grid_constant__ RolloutArgs a) {
@@ -117,23 +117,30 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd2_kernel(const __grid_
             double dzg, pad, dax, day;
             rec.load2(8, dzg, pad);
             rec.load2(9, dax, day);
-            double* dst = jring + (size_t)(j & 1) * kJLen * kBwdBlock;
+            double* dst = jring + (size_t)(j & (kRing - 1)) * kJLen * kBwdBlock;
             *reinterpret_cast<double2*>(dst) = make_double2(jr[0][0], jr[1][0]);                  // jxx jyx
             *reinterpret_cast<double2*>(dst + 2 * kBwdBlock) = make_double2(jr[0][1], jr[1][1]);  // jxy jyy
             *reinterpret_cast<double2*>(dst + 4 * kBwdBlock) = make_double2(dzg, 0.0);
             *reinterpret_cast<double2*>(dst + 6 * kBwdBlock) = make_double2(dax, day);
-            bar_arrive64(kBarEmpty + (int)(j & 1));
+            bar_arrive64(kBarEmpty + (int)(j & (kRing - 1)));
         };
-        prefetch(0, 0);
-        prefetch(1, 1);
+        // The consumer runs kLook = kRing - 2 stages ahead with J: J depends on the stored activations only, so while the producer
+        // is held up (every 40th stage it also evaluates the row loss: ~1.7 stage times) the consumer keeps forming Jacobians, and
+        // afterwards the producer finds them ready and catches up while the consumer works off the weight gradients.  With a
+        // lead of one stage (round 1) each warp waited on the other in turn (5 % / 12 % of their time).  Ring safety: J(i) is
+        // published after F(i - kLook - 1) has been consumed (at least kRing stages would do), F(i) is staged after J(i) has
+        // been read.  Stage j lives in tile j mod kTiles (kTiles = kLook + 2 = kRing, a power of two: no index registers).
+#pragma unroll 1
+        for (int i = 0; i <= kLook; i++) prefetch(i, i);
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-        publish_jac(0, 0);
-        int t0 = 0, t1 = 1, t2 = 2;  // tiles of reverse stages j, j+1, j+2
+#pragma unroll 1
+        for (int i = 0; i < kLook; i++) if (i < nrec) publish_jac(i, i);
 #pragma unroll 1
         for (long j = 0; j < nrec; j++) {
-            prefetch(j + 2, t2);
-            if (j + 1 < nrec) publish_jac(j + 1, t1);
-            const int q = (int)(j & 1);
+            const int t0 = (int)(j & (kTiles - 1));
+            prefetch(j + kLook + 1, (int)((j + kLook + 1) & (kTiles - 1)));
+            if (j + kLook < nrec) publish_jac(j + kLook, (int)((j + kLook) & (kTiles - 1)));
+            const int q = (int)(j & (kRing - 1));
             bar_sync64(kBarFull + q);
             const double* f = fring + (size_t)q * kFLen * kBwdBlock;
             const double fxb = f[0], fyb = f[kBwdBlock], s1 = f[2 * kBwdBlock], s2 = f[3 * kBwdBlock], s3 = f[4 * kBwdBlock];
@@ -183,7 +190,6 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd2_kernel(const __grid_
                 }
             }
             asm volatile("cp.async.wait_group 0;" ::: "memory");
-            const int tt = t0; t0 = t1; t1 = t2; t2 = tt;
         }
 #pragma unroll
         for (int k = 0; k < kOffW4; k++) {

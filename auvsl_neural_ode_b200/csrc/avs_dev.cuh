@@ -146,7 +146,12 @@ template <int TERR, int BLOCK, bool STORE> struct FusedStep {
 };
 
 // ---- named barriers of the warp-specialised reverse kernel (producer warp + consumer warp, 64 participants) -----------
-constexpr int kBarFull = 1, kBarEmpty = 3;
+#ifndef AVS_BWD_RING
+#define AVS_BWD_RING 4
+#endif
+constexpr int kRing = AVS_BWD_RING;  // depth of the J and F rings (power of two): the consumer forms J kRing - 2 stages ahead
+static_assert(kRing >= 4 && (kRing & (kRing - 1)) == 0 && 2 * kRing + 1 <= 16, "ring depth");
+constexpr int kBarFull = 1, kBarEmpty = 1 + kRing;
 __device__ __forceinline__ void bar_sync64(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void bar_arrive64(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 
@@ -179,9 +184,9 @@ template <int BLOCK> struct ActInSmem {
 // ---- reverse kernel, split tire adjoint (rollout_bwd2_kernel) ---------------------------------------------------------
 // Consumer -> producer: per lane and stage the xy-net Jacobian, the gated z derivative and the terrain gradient
 // (kJLen doubles as four 16-byte pairs: jxx jyx | jxy jyy | dzg - | dax day), formed one stage AHEAD of the producer.
-// Producer -> consumer: Fx_bar Fy_bar s1 s2 s3 (kFLen columns).  Both rings are two deep (stage parity).
-// Named barriers: kBarFull + q = "F of a parity-q stage is staged" (producer arrives, consumer syncs),
-//                 kBarEmpty + q = "J of a parity-q stage is ready" (consumer arrives, producer syncs).  Because the consumer
+// Producer -> consumer: Fx_bar Fy_bar s1 s2 s3 (kFLen columns).  Both rings are kRing deep (slot q = stage mod kRing).
+// Named barriers: kBarFull + q = "F of a slot-q stage is staged" (producer arrives, consumer syncs),
+//                 kBarEmpty + q = "J of a slot-q stage is ready" (consumer arrives, producer syncs).  Because the consumer
 // publishes J of stage i+1 only after it has consumed F of stage i-1, and the producer stages F of stage i only after it has
 // read J of stage i, those two hand-shakes also protect the reuse of both rings.
 constexpr int kJLen = 8, kFLen = 5;
@@ -189,7 +194,7 @@ template <int BLOCK> struct JInSmem {
     const double* ring0;  // pair 0 of this lane in J buffer 0
     int count;
     __device__ __forceinline__ void get(int, TireJac& J, double& dzg, double& dax, double& day) const {
-        const int q = count & 1;
+        const int q = count & (kRing - 1);
         bar_sync64(kBarEmpty + q);
         const double* b = ring0 + (size_t)q * kJLen * BLOCK;
         const double2 p0 = *reinterpret_cast<const double2*>(b), p1 = *reinterpret_cast<const double2*>(b + 2 * BLOCK),
@@ -201,7 +206,7 @@ template <int BLOCK> struct FOutSmem {
     double* ring0;  // column 0 of this lane in F buffer 0
     int count;
     __device__ __forceinline__ void put(int, double fxb, double fyb, double s1, double s2, double s3) const {
-        const int q = count & 1;
+        const int q = count & (kRing - 1);
         double* dst = ring0 + (size_t)q * kFLen * BLOCK;
         dst[0] = fxb; dst[BLOCK] = fyb; dst[2 * BLOCK] = s1; dst[3 * BLOCK] = s2; dst[4 * BLOCK] = s3;
         bar_arrive64(kBarFull + q);
