@@ -8,8 +8,9 @@ namespace avs {
 // non-inlined stage callee (163-168 registers, 1 % back-to-back dependent FP64); without it ptxas settles on 128 registers and a
 // more serial order (measured: forward+store 14.1 ms vs 11.5 ms at N = 4096 x T = 200).
 // MINB = resident CTAs per SM the register cap is computed for.  The instantiation that also stores the adjoint's records runs at
-// that cap; with the cap of two CTAs (188 registers) it is 2 % faster while two CTAs per SM hold the whole launch (11.09 ->
-// 10.89 ms at N = 4096, 18.0 -> 17.6 at 8192) and 2 % slower beyond (34.3 against 33.6 ms at 16 384): launch_fwd_t picks by size.
+// that cap; with the cap of two CTAs (188 registers; forward only: 176) it is 2 % faster while two CTAs per SM hold the whole
+// launch (11.09 -> 10.89 ms at N = 4096, 18.0 -> 17.6 at 8192) and 2 % slower beyond (34.3 against 33.6 ms at 16 384):
+// launch_fwd_t picks by size.
 // MARGIN (Bekker only): diagnostic instantiation that also reports the branch margins of every trajectory (avs_bekker.cuh)
 template <int TIRE, int TERR, bool STORE, bool MARGIN = false, int MINB = 3>
 __global__ void __launch_bounds__(kFwdBlock, (TIRE == TIRE_NN ? MINB * (128 / kFwdBlock) : 0)) rollout_fwd_kernel(const __grid_constant__ RolloutArgs a) {
@@ -68,15 +69,16 @@ static cudaError_t launch_fwd_k(const ModelConst& mc, const double* d_live, cons
 }
 template <int TIRE, int TERR, bool STORE, bool MARGIN = false>
 static cudaError_t launch_fwd_t(const ModelConst& mc, const double* d_live, const RolloutArgs& a, cudaStream_t s) {
-    if (TIRE == TIRE_NN && STORE) {
-        // the 188-register build while two CTAs per SM hold the whole launch, the 168-register build beyond
+    if (TIRE == TIRE_NN) {
+        // the build with the register cap of two CTAs per SM while two CTAs per SM hold the whole launch (forward only: 176
+        // registers, 28.04 -> 27.53 ms at 4096 x 600 rows; forward + store: 188 registers), the three-CTA build beyond
         static int sms = 0;
         if (sms == 0) {
             int dev = 0;
             if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
         }
         const long long ctas = ((long long)a.Nc * 4 + kFwdBlock - 1) / kFwdBlock;
-        if (ctas <= 2LL * sms * (128 / kFwdBlock)) return launch_fwd_k<TIRE, TERR, STORE, MARGIN, (TIRE == TIRE_NN && STORE) ? 2 : 3>(mc, d_live, a, s);
+        if (ctas <= 2LL * sms * (128 / kFwdBlock)) return launch_fwd_k<TIRE, TERR, STORE, MARGIN, TIRE == TIRE_NN ? 2 : 3>(mc, d_live, a, s);
     }
     return launch_fwd_k<TIRE, TERR, STORE, MARGIN, 3>(mc, d_live, a, s);
 }
