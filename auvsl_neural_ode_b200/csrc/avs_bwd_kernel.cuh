@@ -1,16 +1,18 @@
 // avs_bwd_kernel.cuh — reverse-sweep (BPTT) kernel templates (instantiated in avs_k_bwd_*.cu)
 //
 // They replace the CppAD tape + ADFun::Reverse(1) of Trainer::trainTrajectory (/root/reference/src/Trainer.cpp:607-657).
-// A CTA is two warps serving the same 8 vehicles x 4 wheel lanes; the loop-carried adjoints live in shared-memory scratch
-// columns (conflict-free: consecutive lanes -> consecutive banks); at the end the consumer sums the 4 wheel lanes of a
-// vehicle (shuffles) and writes gps[104][N], the producer writes loss[N].
+// A CTA is two warps serving the same 8 vehicles x 4 wheel lanes.  The loop-carried adjoints (LAM, YB, KB) and the staged state
+// records are vehicle-level data shared by the four lanes of a vehicle: they live in shared memory as 8-vehicle tiles (seven
+// 16-byte pairs per vehicle, read by broadcast).  At the end the consumer sums the 4 wheel lanes of a vehicle (shuffles) and
+// writes gps[104][N], the producer writes loss[N].
 //
 //   rollout_bwd2_kernel: tire adjoint split between the warps.
-//     * producer — state-record stream (cp.async one stage ahead), adjoint of the base link, the ABA wheel passes, contact
-//       geometry / terrain gradient, quaternion normalisations; through the tire network only J^T F_bar with the 2x2 Jacobian
-//       the consumer formed a stage ahead; stages 5 values per wheel for the weight gradient;
-//     * consumer — activation-record stream (own cp.async ring, three tiles), Jacobian of the NEXT stage, layered
-//       back-propagation + three outer products of the current stage into dL/dW (104 doubles per lane in registers).
+//     * producer — state-tile stream (two contiguous cp.async one stage ahead), adjoint of the base link, the ABA wheel passes,
+//       contact geometry / terrain gradient, quaternion normalisations, inlined into the stage loop; through the tire network only
+//       J^T F_bar with the 2x2 Jacobian the consumer formed ahead of it; stages 5 values per wheel for the weight gradient;
+//     * consumer — activation-record stream (own cp.async ring of kTiles tiles), Jacobians kLook stages AHEAD of the producer,
+//       layered back-propagation + three outer products of the current stage into dL/dW (88 accumulators per lane in registers,
+//       the 16 of dW4 in shared memory).
 //   (The previous cut — producer runs the whole tire adjoint and stages the 37 outer-product operands, consumer only
 //   accumulates — took 14.9 ms against 12.3 ms at N = 4096 x T = 200 and was removed)
 #pragma once
@@ -21,10 +23,9 @@ namespace avs {
 constexpr int kBwdThreads = 2 * kBwdBlock;  // producer warp + consumer warp
 
 // ---- split tire adjoint ------------------------------------------------------------------------------------------------
-// Same two roles, different cut: the producer's state chain uses the xy-net Jacobian the consumer formed a stage ahead
-// (3x3 worth of FMAs instead of the layered back-propagation, 5 staged values instead of 37, no activation traffic), the
-// consumer owns the activation stream (own cp.async ring, three tiles deep), forms J, runs the layered back-propagation for
-// the weight gradient and accumulates the outer products.
+// The producer's state chain uses the xy-net Jacobian the consumer formed ahead of it (3x3 worth of FMAs instead of the layered
+// back-propagation, 5 staged values instead of 37, no activation traffic); the consumer owns the activation stream, forms J,
+// runs the layered back-propagation for the weight gradient and accumulates the outer products.
 // shared memory, in columns of kBwdBlock doubles: adjoint tiles LAM | YB | KB (3 x kCkTile doubles) 0 | state tile A 11 |
 // state tile B 15 | activation tiles 19 (kTiles x kActLen columns) | J ring | F ring | dW4
 constexpr int kB2SlotRecA = 11, kB2SlotRecB = 15, kB2SlotT = 19, kLook = kRing - 2, kTiles = kRing, kB2SlotJ = kB2SlotT + kTiles * kActLen, kB2SlotF = kB2SlotJ + kRing * kJLen, kB2SlotG4 = kB2SlotF + kRing * kFLen, kB2Slots = kB2SlotG4 + 16;  // + dW4 accumulators (16 per lane, as 8 pairs)

@@ -189,9 +189,6 @@ template <int BLOCK> struct PairCol {
     // the 13-vector that starts c0 scalar slots later (vectors are padded to 7 pairs = 14 slots): sub(13) = next vector
     __device__ __forceinline__ PairCol sub(int c0) const { return PairCol{base + (size_t)(c0 / 13) * 14 * BLOCK}; }
 };
-template <int BLOCK> __device__ __forceinline__ PairCol<BLOCK> pair_col(int slot) {
-    return PairCol<BLOCK>{g_smem + (size_t)slot * BLOCK + (size_t)threadIdx.x * 2};
-}
 
 // activation record staged in shared memory as ten 16-byte pairs: pair i of this lane at base[i * BLOCK * 2]
 template <int BLOCK> struct ActInSmem {

@@ -9,7 +9,7 @@ namespace avs {
 #define AVS_FWD_BLOCK 128
 #endif
 constexpr int kFwdBlock = AVS_FWD_BLOCK;  // threads per CTA, forward rollout (scratch columns are per thread: any multiple of 32 works)
-constexpr int kBwdBlock = 32;   // (vehicle, wheel) lanes per CTA of the reverse sweep; the CTA has 2 warps (producer + consumer), 44.5 KB smem, 4 CTAs per SM
+constexpr int kBwdBlock = 32;   // (vehicle, wheel) lanes per CTA of the reverse sweep; the CTA has 2 warps (producer + consumer), 42 KB smem, 255 registers: 4 CTAs per SM
 
 // forward rollout: one vehicle per 4-lane group (lane = wheel)
 cudaError_t launch_fwd_nn_flat(bool store, const ModelConst& mc, const double* d_live, const RolloutArgs& a, cudaStream_t s);
