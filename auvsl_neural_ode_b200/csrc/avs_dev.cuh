@@ -166,6 +166,104 @@ template <int TERR, int BLOCK, bool STORE> struct FusedStep {
     }
 };
 
+
+// ---- forward stage on vehicle-shared tiles ---------------------------------------------------------------------------------
+// The loop-carried 13-vectors of the forward sweep (X, ACC, T) are vehicle-level data that the four lanes of a vehicle hold as
+// bit-identical copies.  Here they live ONCE per vehicle, in tiles of the state-record shape (kCkTile doubles per warp: pair r
+// of vehicle v at r*16 + v*2): the four lanes store the same 16 bytes to the same address and read them back by broadcast (one
+// shared-memory wavefront per LDS.128 / STS.128 of the warp), and the T tile with the inverse norm in its slot 13 IS the
+// stage's state record, so the record store is a coalesced copy of 896 contiguous bytes by all 32 lanes instead of seven
+// STG.128 of eight writer lanes in a divergent region.  Per warp: X | ACC | T | - | joint positions.
+// Used by the instantiation that stores the adjoint's records (forward + store 10.89 -> 10.59 ms at N = 4096 x T = 200, round 2);
+// the forward-only instantiation keeps the per-thread columns below (on tiles it is 3 % slower: 28.47 against 27.53 ms).
+constexpr int kFwdTileSet = 5 * kCkTile;
+struct TileCol {
+    double* p;  // pair 0 of this lane's vehicle
+    __device__ __forceinline__ double& operator[](int c) const { return p[(size_t)(c >> 1) * kCkPairStride + (c & 1)]; }
+    __device__ __forceinline__ TileCol sub(int c0) const { return TileCol{p + (size_t)(c0 / 13) * kCkTile}; }
+};
+__device__ __forceinline__ TileCol fwd_tile_col(int tid) { return TileCol{g_smem + (size_t)(tid >> 5) * kFwdTileSet + ((tid & 31) >> 2) * 2}; }
+template <int TERR, int BLOCK, bool STORE>
+__device__ __noinline__ void ode_fwd_stage_call_tiles(int tid, int lane0, double ul, double ur, int s, double* rec_tile, double* act) {
+    double* const wbase = g_smem + (size_t)(tid >> 5) * kFwdTileSet;
+    double* const Xt = wbase + ((tid & 31) >> 2) * 2;
+    double* const At = Xt + kCkTile;
+    double* const Tt = Xt + 2 * kCkTile;
+    double x[14], k[13];
+#pragma unroll
+    for (int i = 0; i < 7; i++) { const double2 v = *reinterpret_cast<const double2*>(Tt + i * kCkPairStride); x[2 * i] = v.x; x[2 * i + 1] = v.y; }
+    if (STORE && rec_tile) {  // warp-uniform
+        const int l = tid & 31;
+        const double* src = wbase + 2 * kCkTile + l * 2;
+        *reinterpret_cast<double2*>(rec_tile + l * 2) = *reinterpret_cast<const double2*>(src);
+        if (l < kCkTile / 2 - 32) *reinterpret_cast<double2*>(rec_tile + 64 + l * 2) = *reinterpret_cast<const double2*>(src + 64);
+    }
+    ode_fwd<1, TIRE_NN, TERR, STORE>(c_mc, lane0, x, ul, ur, k, nullptr, ActOutPtr{act, kActPairStride});
+    const double h = kDt;
+    double inv;
+    double X[14];
+#pragma unroll
+    for (int i = 0; i < 7; i++) { const double2 v = *reinterpret_cast<const double2*>(Xt + i * kCkPairStride); X[2 * i] = v.x; X[2 * i + 1] = v.y; }
+    if (s < 3) {
+        const double wgt = (s == 0) ? 1.0 : 2.0;   // k1 + 2 k2 + 2 k3 + k4
+        const double cs = (s == 2) ? h : .5 * h;   // X + .5h k1, X + .5h k2, X + h k3
+        double acc[14];
+        acc[13] = 0.0;
+        if (s == 0) {
+#pragma unroll
+            for (int c = 0; c < 13; c++) acc[c] = fma(wgt, k[c], 0.0);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 7; i++) { const double2 v = *reinterpret_cast<const double2*>(At + i * kCkPairStride); acc[2 * i] = v.x; acc[2 * i + 1] = v.y; }
+#pragma unroll
+            for (int c = 0; c < 13; c++) acc[c] = fma(wgt, k[c], acc[c]);
+        }
+#pragma unroll
+        for (int i = 0; i < 7; i++) *reinterpret_cast<double2*>(At + i * kCkPairStride) = make_double2(acc[2 * i], acc[2 * i + 1]);
+#pragma unroll
+        for (int c = 0; c < 13; c++) x[c] = fma(cs, k[c], X[c]);
+        renorm(x, inv);
+    } else {
+        double acc[14];
+#pragma unroll
+        for (int i = 0; i < 7; i++) { const double2 v = *reinterpret_cast<const double2*>(At + i * kCkPairStride); acc[2 * i] = v.x; acc[2 * i + 1] = v.y; }
+#pragma unroll
+        for (int c = 0; c < 13; c++) x[c] = fma(h / 6.0, fma(1.0, k[c], acc[c]), X[c]);
+        renorm(x, inv);
+#pragma unroll
+        for (int i = 0; i < 6; i++) *reinterpret_cast<double2*>(Xt + i * kCkPairStride) = make_double2(x[2 * i], x[2 * i + 1]);
+        *reinterpret_cast<double2*>(Xt + 6 * kCkPairStride) = make_double2(x[12], 0.0);
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++) *reinterpret_cast<double2*>(Tt + i * kCkPairStride) = make_double2(x[2 * i], x[2 * i + 1]);
+    *reinterpret_cast<double2*>(Tt + 6 * kCkPairStride) = make_double2(x[12], inv);
+    __syncwarp();  // the T tile is copied out by all lanes at the head of the next stage
+}
+template <int TERR, int BLOCK, bool STORE> struct FusedStepTiles {
+    const RolloutArgs& a;
+    int n, lane0;
+    bool writer;
+    double ul, ur;
+    __device__ __forceinline__ void operator()(size_t step, double& inv_carry) const {
+        const size_t NK = (size_t)a.Nc;
+        const size_t rec_stride = ck_rec_stride(NK);
+        const size_t gidx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+        const bool warp_valid = (gidx >> 5) * kCkTileVeh < NK;  // the warp's first vehicle exists: its state tile does
+        double* rec = (STORE && warp_valid) ? a.ckpt + (step * 4) * rec_stride + (gidx >> 5) * kCkTile : nullptr;
+        const size_t act_stride = act_stage_doubles(NK);
+        double* act = STORE ? a.act + (step * 4) * act_stride + act_lane_offset(gidx) : nullptr;
+        const int tid = (int)threadIdx.x;
+        if (STORE) {
+            AVS_DBG_RANGE("state tiles of a step (store)", rec, 3 * rec_stride + kCkTile, a.ckpt, a.ckpt_doubles);
+            AVS_DBG_RANGE("activation records of a step (store)", act, 3 * act_stride + 9 * kActPairStride + 2, a.act, a.act_doubles);
+        }
+#pragma unroll 1
+        for (int s = 0; s < 4; s++)
+            ode_fwd_stage_call_tiles<TERR, BLOCK, STORE>(tid, lane0, ul, ur, s, rec ? rec + (size_t)s * rec_stride : nullptr, STORE ? act + (size_t)s * act_stride : nullptr);
+        inv_carry = fwd_tile_col(tid).sub(26)[13];
+    }
+};
+
 // ---- named barriers of the warp-specialised reverse kernel (producer warp + consumer warp, 64 participants) -----------
 #ifndef AVS_BWD_RING
 #define AVS_BWD_RING 4

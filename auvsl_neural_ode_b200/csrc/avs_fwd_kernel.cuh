@@ -22,15 +22,29 @@ __global__ void __launch_bounds__(kFwdBlock, (TIRE == TIRE_NN ? MINB * (128 / kF
     const Scratch<kFwdBlock> S = scratch_col<kFwdBlock>(0);
     const bool writer = (lane0 == 0) && valid;
     if (TIRE == TIRE_NN) {
-        // fused stages: T starts as a copy of X, the carried inverse norm as 1
-        {
-            const size_t N = (size_t)a.N;
+        if (STORE) {
+            // forward + store: fused stages on vehicle-shared tiles (avs_dev.cuh): T starts as a copy of X, the carried inverse norm as 1
+            const TileCol ST = fwd_tile_col((int)threadIdx.x);
+            {
+                const size_t N = (size_t)a.N;
+                const TileCol TT = ST.sub(26);
 #pragma unroll
-            for (int c = 0; c < 13; c++) S[26 + c] = __ldg(a.x0 + (size_t)live_to_ref(c) * N + n);
-            S[56] = 1.0;
+                for (int c = 0; c < 13; c++) TT[c] = __ldg(a.x0 + (size_t)live_to_ref(c) * N + n);
+                TT[13] = 1.0;
+            }
+            auto mk_step = [&a, n, lane0, writer](double ul, double ur) { return FusedStepTiles<TERR, kFwdBlock, STORE>{a, n, lane0, writer, ul, ur}; };
+            rollout_fwd_body<STORE>(a, n, lane0, valid, ST, mk_step);
+        } else {
+            // forward only: fused stages on per-thread scratch columns: T starts as a copy of X, the carried inverse norm as 1
+            {
+                const size_t N = (size_t)a.N;
+#pragma unroll
+                for (int c = 0; c < 13; c++) S[26 + c] = __ldg(a.x0 + (size_t)live_to_ref(c) * N + n);
+                S[56] = 1.0;
+            }
+            auto mk_step = [&a, n, lane0, writer](double ul, double ur) { return FusedStep<TERR, kFwdBlock, STORE>{a, n, lane0, writer, ul, ur}; };
+            rollout_fwd_body<STORE>(a, n, lane0, valid, S, mk_step);
         }
-        auto mk_step = [&a, n, lane0, writer](double ul, double ur) { return FusedStep<TERR, kFwdBlock, STORE>{a, n, lane0, writer, ul, ur}; };
-        rollout_fwd_body<STORE>(a, n, lane0, valid, S, mk_step);
     } else {
         const size_t stage_stride = (size_t)4 * a.Nc * kActLen;
         const Scratch<kFwdBlock> M = scratch_col<kFwdBlock>(kFwdScratch + kBekScratch);
@@ -59,7 +73,9 @@ template <int TIRE, int TERR, bool STORE, bool MARGIN, int MINB>
 static cudaError_t launch_fwd_k(const ModelConst& mc, const double* d_live, const RolloutArgs& a, cudaStream_t s) {
     const long long threads = (long long)a.Nc * 4;
     const int grid = (int)((threads + kFwdBlock - 1) / kFwdBlock);
-    const size_t smem = (size_t)(kFwdScratch + (TIRE == TIRE_BEKKER ? kBekScratch : 0) + (MARGIN ? kNumMargins : 0)) * kFwdBlock * sizeof(double);
+    // forward + store keeps its loop-carried vectors in vehicle-shared tiles (one set per warp), everything else in per-thread columns
+    const size_t smem = (TIRE == TIRE_NN && STORE) ? (size_t)(kFwdBlock / 32) * kFwdTileSet * sizeof(double)
+                                                   : (size_t)(kFwdScratch + (TIRE == TIRE_BEKKER ? kBekScratch : 0) + (MARGIN ? kNumMargins : 0)) * kFwdBlock * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(rollout_fwd_kernel<TIRE, TERR, STORE, MARGIN, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     e = upload_model(mc, d_live, s);
