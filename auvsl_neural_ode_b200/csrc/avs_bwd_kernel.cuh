@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd2_kernel(const __grid_
                 AVS_DBG_RANGE("activation record (reverse prefetch)", src, 9 * kActPairStride + 2, a.act, a.act_doubles);
                 double* dst = tile_of(t);
 #pragma unroll
-                for (int i = 0; i < kActLen / 2; i++) {
+                for (int i = 0; i < (TERR == TERR_FLAT ? kActLen / 2 - 1 : kActLen / 2); i++) {  // flat: pair 9 (terrain gradient) is not stored
                     const unsigned saddr = (unsigned)__cvta_generic_to_shared(dst + (size_t)i * kBwdBlock * 2);
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(src + (size_t)i * kActPairStride) : "memory");
                 }
@@ -115,9 +115,9 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd2_kernel(const __grid_
                 jr[r][0] = -(a0 + b0) * (os / kInStd1);
                 jr[r][1] = (a2 + b2) * (os / kInStd3);
             }
-            double dzg, pad, dax, day;
+            double dzg, pad, dax = 0.0, day = 0.0;
             rec.load2(8, dzg, pad);
-            rec.load2(9, dax, day);
+            if (TERR != TERR_FLAT) rec.load2(9, dax, day);
             double* dst = jring + (size_t)(j & (kRing - 1)) * kJLen * kBwdBlock;
             *reinterpret_cast<double2*>(dst) = make_double2(jr[0][0], jr[1][0]);                  // jxx jyx
             *reinterpret_cast<double2*>(dst + 2 * kBwdBlock) = make_double2(jr[0][1], jr[1][1]);  // jxy jyy

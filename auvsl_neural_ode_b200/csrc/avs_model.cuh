@@ -799,11 +799,14 @@ struct ActInPtr {
     AVS_HD void load2(int i, double& a, double& b) const { a = p[2 * i]; b = p[2 * i + 1]; }
     AVS_HD ActInPtr wheel(int k) const { return ActInPtr{p + (size_t)k * kActLen}; }
 };
-template <class AOut> AVS_HD void act_store(const NNAct& a, double dax, double day, const AOut& o) {
+// WITH_SLOPE = false (flat-terrain instantiation): the terrain gradient is identically 0 and the adjoint never reads it, so pair 9
+// is neither written nor fetched (its slot stays in the layout: one STG.128 / cp.async per lane and stage and 10 % of the
+// activation traffic less)
+template <bool WITH_SLOPE = true, class AOut> AVS_HD void act_store(const NNAct& a, double dax, double day, const AOut& o) {
 #pragma unroll
     for (int j = 0; j < 4; j++) { o.store2(j, a.h0[2 * j], a.h0[2 * j + 1]); o.store2(4 + j, a.h2[2 * j], a.h2[2 * j + 1]); }
     o.store2(8, a.z4 > 0.0 ? a.dz4 : 0.0, 0.0);
-    o.store2(9, dax, day);
+    if (WITH_SLOPE) o.store2(9, dax, day);
 }
 template <class AIn> AVS_HD void act_load(NNAct& a, double& dax, double& day, const AIn& in) {
 #pragma unroll
@@ -1121,7 +1124,11 @@ AVS_HD void ode_fwd(const ModelConst& mc, int lane0, const double X[13], double 
         if (TIRE == TIRE_NN) {
             tire_nn_fwd<STORE_ACT>(mc, cv[0], cv[1], wsp, sink, F, act.nn);
             F[2] = fma(kNNDamp, cv[2], F[2]);
-            if (STORE_ACT) act_store(act.nn, dax, day, act_out.wheel(k));
+#if defined(__CUDA_ARCH__)
+            if (STORE_ACT) act_store<TERR != TERR_FLAT>(act.nn, dax, day, act_out.wheel(k));
+#else
+            if (STORE_ACT) act_store(act.nn, dax, day, act_out.wheel(k));  // the host harness reads whole records
+#endif
         } else {
             bekker_tire_fwd<TERR>(mc, cv[0], cv[1], wsp, sink, cp, F, bek_eval);
             F[2] = fma(kBekkerDamp, cv[2], F[2]);
