@@ -1,3 +1,3 @@
-python -m pytest tests -x -q -m gpu > gpurun_out/r2_gputest5.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/r2_gputest5.log
-python scripts/ncu_targets.py once > gpurun_out/ncu_targets_plain.log 2>&1; echo "targets rc=$?"; tail -1 gpurun_out/ncu_targets_plain.log
-ncu --set full --metrics smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,sm__inst_executed_pipe_fp64.sum --clock-control none --import-source on -k regex:rollout -c 4 -f -o gpurun_out/prof_r2e python scripts/ncu_targets.py once > gpurun_out/ncu_r2e.log 2>&1; echo "ncu rc=$?"
+python bench.py > gpurun_out/bench_r2f.json 2> gpurun_out/bench_r2f.err; echo "bench rc=$?"; tail -2 gpurun_out/bench_r2f.err
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r2.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch_r2.log 2>&1; echo "ncu launches rc=$?"
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
