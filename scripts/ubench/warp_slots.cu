@@ -6,14 +6,15 @@
 #include <vector>
 #include <map>
 extern __shared__ double sm[];
-__global__ void __launch_bounds__(64, 4) probe(int* out, int spin) {
+__global__ void probe(int* out, int spin) {
     unsigned smid, warpid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     asm volatile("mov.u32 %0, %%warpid;" : "=r"(warpid));
     sm[threadIdx.x] = threadIdx.x;
     long long t0 = clock64();
     while (clock64() - t0 < spin) {}
-    if ((threadIdx.x & 31) == 0) { out[(blockIdx.x * 2 + (threadIdx.x >> 5)) * 2] = smid; out[(blockIdx.x * 2 + (threadIdx.x >> 5)) * 2 + 1] = warpid; }
+    const int wpb = blockDim.x >> 5, w = blockIdx.x * wpb + (threadIdx.x >> 5);
+    if ((threadIdx.x & 31) == 0) { out[w * 2] = smid; out[w * 2 + 1] = warpid; }
 }
 int main(int argc, char** argv) {
     int threads = argc > 1 ? atoi(argv[1]) : 64, blocks = argc > 2 ? atoi(argv[2]) : 512, regs_smem = argc > 3 ? atoi(argv[3]) : 44 * 1024;
