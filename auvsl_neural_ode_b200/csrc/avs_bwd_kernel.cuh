@@ -6,15 +6,19 @@
 // 16-byte pairs per vehicle, read by broadcast).  At the end the consumer sums the 4 wheel lanes of a vehicle (shuffles) and
 // writes gps[104][N], the producer writes loss[N].
 //
-//   rollout_bwd2_kernel: tire adjoint split between the warps.
+//   rollout_bwd2_kernel:
 //     * producer — state-tile stream (two contiguous cp.async one stage ahead), adjoint of the base link, the ABA wheel passes,
-//       contact geometry / terrain gradient, quaternion normalisations, inlined into the stage loop; through the tire network only
-//       J^T F_bar with the 2x2 Jacobian the consumer formed ahead of it; stages 5 values per wheel for the weight gradient;
-//     * consumer — activation-record stream (own cp.async ring of kTiles tiles), Jacobians kLook stages AHEAD of the producer,
-//       layered back-propagation + three outer products of the current stage into dL/dW (88 accumulators per lane in registers,
-//       the 16 of dW4 in shared memory).
-//   (The previous cut — producer runs the whole tire adjoint and stages the 37 outer-product operands, consumer only
-//   accumulates — took 14.9 ms against 12.3 ms at N = 4096 x T = 200 and was removed)
+//       contact geometry / terrain gradient, quaternion normalisations AND the layered back-propagation of the tire network
+//       (ode_bwd_nn_p), inlined into the stage loop; it reads the activations from the consumer's tile of the stage and stages
+//       the 21 operands of the weight-gradient outer products;
+//     * consumer — activation-record stream (own cp.async ring of kTiles tiles, kLook stages ahead of the producer) and the
+//       three outer products of the current stage into dL/dW: 104 accumulators per lane in registers.
+//   CTAs on the upper warp slots of an SM swap the roles of their warps, so that every scheduler serves one producer and one
+//   consumer (AVS_BWD_SWAP): both rollout kernels are bound by issue slots, and the two roles are unequal now.
+//   History: (1) producer runs the whole tire adjoint and stages 37 operands, consumer only accumulates: 14.9 ms at N = 4096 x
+//   T = 200; (2) consumer forms the 2x2 Jacobian of the xy-net a stage ahead, producer multiplies by it, consumer repeats the
+//   layered pass for the weight gradient: 12.3 -> 10.65 ms after the round's tuning — but ~210 FP64 instructions per wheel and
+//   stage more than (3), this one.  DESIGN.md §4 / §7b.
 #pragma once
 #include "avs_dev.cuh"
 
@@ -22,13 +26,9 @@ namespace avs {
 
 constexpr int kBwdThreads = 2 * kBwdBlock;  // producer warp + consumer warp
 
-// ---- split tire adjoint ------------------------------------------------------------------------------------------------
-// The producer's state chain uses the xy-net Jacobian the consumer formed ahead of it (3x3 worth of FMAs instead of the layered
-// back-propagation, 5 staged values instead of 37, no activation traffic); the consumer owns the activation stream, forms J,
-// runs the layered back-propagation for the weight gradient and accumulates the outer products.
 // shared memory, in columns of kBwdBlock doubles: adjoint tiles LAM | YB | KB (3 x kCkTile doubles) 0 | state tile A 11 |
-// state tile B 15 | activation tiles 19 (kTiles x kActLen columns) | J ring | F ring | dW4
-constexpr int kB2SlotRecA = 11, kB2SlotRecB = 15, kB2SlotT = 19, kLook = kRing - 2, kTiles = kRing, kB2SlotJ = kB2SlotT + kTiles * kActLen, kB2SlotF = kB2SlotJ + kRing * kJLen, kB2SlotG4 = kB2SlotF + kRing * kFLen, kB2Slots = kB2SlotG4 + 16;  // + dW4 accumulators (16 per lane, as 8 pairs)
+// state tile B 15 | activation tiles 19 (kTiles x kActLen columns) | operand ring (kRing x kFLen columns)
+constexpr int kB2SlotRecA = 11, kB2SlotRecB = 15, kB2SlotT = 19, kLook = kRing - 2, kTiles = kRing, kB2SlotF = kB2SlotT + kTiles * kActLen, kB2Slots = kB2SlotF + kRing * kFLen;
 
 template <int TERR>
 __global__ void __launch_bounds__(kBwdThreads) rollout_bwd2_kernel(const __grid_constant__ RolloutArgs a) {
@@ -40,13 +40,27 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd2_kernel(const __grid_
     if (!valid) n = a.Nc - 1;
     const bool writer = valid && lane0 == 0;
     const long nrec = (long)(a.T - 1) * a.substeps * 4;
-    if (threadIdx.x < kBwdBlock) {
+#if AVS_BWD_SWAP
+    // hardware warp slot mod 4 = scheduler, and a 2-warp CTA takes two consecutive slots (profiles/r2_ubench.txt): the CTAs on
+    // slots 4..7 of an SM swap roles, so that each scheduler serves one producer and one consumer instead of two of a kind
+    __shared__ int s_swap;
+    if (threadIdx.x == 0) {
+        unsigned wid;
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+        s_swap = (int)((wid >> 2) & 1u);
+    }
+    __syncthreads();
+    const bool is_producer = (threadIdx.x < kBwdBlock) != (s_swap != 0);
+#else
+    const bool is_producer = threadIdx.x < kBwdBlock;
+#endif
+    if (is_producer) {
         // ---------------- producer warp: state adjoint
         double loss;
         int stage_counter = 0;
         const int voff = 2 * (n % kCkTileVeh);  // this lane's vehicle inside the CTA's state tile (tail lanes: the mirrored vehicle)
         auto mk_odeb = [lane0, voff, &stage_counter](double ul, double ur) {
-            return OdeBwdCall2<TERR, kBwdBlock>{lane0, voff, kB2SlotRecA, kB2SlotRecB, 0, kB2SlotJ, kB2SlotF, ul, ur, &stage_counter};
+            return OdeBwdCall2<TERR, kBwdBlock>{lane0, voff, kB2SlotRecA, kB2SlotRecB, 0, kB2SlotT, kB2SlotF, ul, ur, &stage_counter};
         };
         static_assert(kBwdBlock == 4 * kCkTileVeh, "a reverse CTA serves exactly one state tile");
         const size_t rstride = ck_rec_stride(a.Nc);
@@ -56,20 +70,14 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd2_kernel(const __grid_
         rollout_bwd_body(a, n, loss, rec_col<kBwdBlock>(0, voff), st, mk_odeb);
         if (writer) a.loss[n] = loss;
     } else {
-        // ---------------- consumer warp: activation stream, Jacobians one stage ahead, weight gradient
-        double g[kOffW4];
+        // ---------------- consumer warp: activation stream kLook stages ahead, weight gradient
+        double g[kNumLive];
 #pragma unroll
-        for (int k = 0; k < kOffW4; k++) g[k] = 0.0;
-        // dL/dW4 (16 of the 104) lives in shared memory as eight 16-byte pairs per lane: the 88 others take 176 registers and
-        // leave the routines below enough room not to spill
-        double* const g4 = g_smem + (size_t)kB2SlotG4 * kBwdBlock + (size_t)lane * 2;
-#pragma unroll
-        for (int i = 0; i < 8; i++) *reinterpret_cast<double2*>(g4 + (size_t)i * kBwdBlock * 2) = make_double2(0.0, 0.0);
+        for (int k = 0; k < kNumLive; k++) g[k] = 0.0;
         const size_t astride = act_stage_doubles(a.Nc);
         const double* act_last = a.act + (size_t)(nrec - 1) * astride + act_lane_offset(gid);  // reverse stage 0 = last forward stage
         double* const tiles = g_smem + (size_t)kB2SlotT * kBwdBlock + (size_t)lane * 2;
-        double* const jring = g_smem + (size_t)kB2SlotJ * kBwdBlock + (size_t)lane * 2;
-        const double* const fring = g_smem + (size_t)kB2SlotF * kBwdBlock + lane;
+        const double* const fring = g_smem + (size_t)kB2SlotF * kBwdBlock + (size_t)lane * 2;
         auto tile_of = [tiles](int t) { return tiles + (size_t)t * kActLen * kBwdBlock; };
         auto prefetch = [&](long j, int t) {  // activation record of reverse stage j -> tile t
             if (j < nrec) {
@@ -84,125 +92,73 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd2_kernel(const __grid_
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
-        // The accumulators take 208 of the 255 registers, so both consumer routines stream the activations from the tile
-        // (one 16-byte pair at a time) instead of holding them, and work one output row / one layer at a time.
-        auto publish_jac = [&](long j, int t) {  // J of reverse stage j from tile t -> J ring, then signal
-            const ActInSmem<kBwdBlock> rec{tile_of(t)};
-            double jr[2][2];
-#pragma unroll
-            for (int r = 0; r < 2; r++) {
-                double v[8];
-#pragma unroll
-                for (int jj = 0; jj < 4; jj++) {
-                    double ha, hb;
-                    rec.load2(4 + jj, ha, hb);  // h2[2jj], h2[2jj+1]
-                    const double ua = fma(-ha, ha, 1.0) * c_mc.W4[r][2 * jj], ub = fma(-hb, hb, 1.0) * c_mc.W4[r][2 * jj + 1];
-#pragma unroll
-                    for (int k = 0; k < 8; k++) v[k] = (jj == 0) ? c_mc.W2[0][k] * ua : fma(c_mc.W2[2 * jj][k], ua, v[k]);
-#pragma unroll
-                    for (int k = 0; k < 8; k++) v[k] = fma(c_mc.W2[2 * jj + 1][k], ub, v[k]);
-                }
-                double a0 = 0.0, a2 = 0.0, b0 = 0.0, b2 = 0.0;
-#pragma unroll
-                for (int kk = 0; kk < 4; kk++) {
-                    double ha, hb;
-                    rec.load2(kk, ha, hb);  // h0[2kk], h0[2kk+1]
-                    const double wa = v[2 * kk] * fma(-ha, ha, 1.0), wb = v[2 * kk + 1] * fma(-hb, hb, 1.0);
-                    a0 = fma(c_mc.W0[2 * kk][0], wa, a0); a2 = fma(c_mc.W0[2 * kk][2], wa, a2);
-                    b0 = fma(c_mc.W0[2 * kk + 1][0], wb, b0); b2 = fma(c_mc.W0[2 * kk + 1][2], wb, b2);
-                }
-                const double os = (r == 0) ? kOutStd0 : kOutStd1;
-                jr[r][0] = -(a0 + b0) * (os / kInStd1);
-                jr[r][1] = (a2 + b2) * (os / kInStd3);
-            }
-            double dzg, pad, dax = 0.0, day = 0.0;
-            rec.load2(8, dzg, pad);
-            if (TERR != TERR_FLAT) rec.load2(9, dax, day);
-            double* dst = jring + (size_t)(j & (kRing - 1)) * kJLen * kBwdBlock;
-            *reinterpret_cast<double2*>(dst) = make_double2(jr[0][0], jr[1][0]);                  // jxx jyx
-            *reinterpret_cast<double2*>(dst + 2 * kBwdBlock) = make_double2(jr[0][1], jr[1][1]);  // jxy jyy
-            *reinterpret_cast<double2*>(dst + 4 * kBwdBlock) = make_double2(dzg, 0.0);
-            *reinterpret_cast<double2*>(dst + 6 * kBwdBlock) = make_double2(dax, day);
-            bar_arrive64(kBarEmpty + (int)(j & (kRing - 1)));
-        };
-        // The consumer runs kLook = kRing - 2 stages ahead with J: J depends on the stored activations only, so while the producer
-        // is held up (every 40th stage it also evaluates the row loss: ~1.7 stage times) the consumer keeps forming Jacobians, and
-        // afterwards the producer finds them ready and catches up while the consumer works off the weight gradients.  With a
-        // lead of one stage (round 1) each warp waited on the other in turn (5 % / 12 % of their time).  Ring safety: J(i) is
-        // published after F(i - kLook - 1) has been consumed (at least kRing stages would do), F(i) is staged after J(i) has
-        // been read.  Stage j lives in tile j mod kTiles (kTiles = kLook + 2 = kRing, a power of two: no index registers).
+        // The consumer signals that the tile of a stage has landed kLook = kRing - 2 stages ahead of the stage whose weight
+        // gradient it works on: while the producer is held up (every 40th stage it also evaluates the row loss: ~1.7 stage times)
+        // the tiles keep arriving.  Ring safety: the tile of stage i is refilled after the operands of stage i have been consumed,
+        // and those are staged after the producer has read the tile.  Stage j lives in tile j mod kTiles (kTiles = kLook + 2 =
+        // kRing, a power of two: no index registers).
 #pragma unroll 1
         for (int i = 0; i <= kLook; i++) prefetch(i, i);
         asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll 1
-        for (int i = 0; i < kLook; i++) if (i < nrec) publish_jac(i, i);
+        for (int i = 0; i < kLook; i++) if (i < nrec) bar_arrive64(kBarEmpty + i);
 #pragma unroll 1
         for (long j = 0; j < nrec; j++) {
             const int t0 = (int)(j & (kTiles - 1));
             prefetch(j + kLook + 1, (int)((j + kLook + 1) & (kTiles - 1)));
-            if (j + kLook < nrec) publish_jac(j + kLook, (int)((j + kLook) & (kTiles - 1)));
+            if (j + kLook < nrec) bar_arrive64(kBarEmpty + (int)((j + kLook) & (kRing - 1)));  // its tile landed before the last wait
             const int q = (int)(j & (kRing - 1));
             bar_sync64(kBarFull + q);
-            const double* f = fring + (size_t)q * kFLen * kBwdBlock;
-            const double fxb = f[0], fyb = f[kBwdBlock], s1 = f[2 * kBwdBlock], s2 = f[3 * kBwdBlock], s3 = f[4 * kBwdBlock];
-            {
-                const ActInSmem<kBwdBlock> rec{tile_of(t0)};
-                const double o0 = fxb * kOutStd0, o1 = fyb * kOutStd1;
-                // layer 4: dW4 += o (x) h2 ; delta2 = (1 - h2^2) . W4^T o
-                double d2[8];
+            const ActInSmem<kBwdBlock> rec{tile_of(t0)};
+            const ActInSmem<kBwdBlock> ops{fring + (size_t)q * kFLen * kBwdBlock};
+            {   // dW4 += (o0, o1) (x) h2
+                double o0, o1;
+                ops.load2(0, o0, o1);
 #pragma unroll
                 for (int jj = 0; jj < 4; jj++) {
                     double ha, hb;
                     rec.load2(4 + jj, ha, hb);
-                    {   // pair jj = (dW4[0][2jj], dW4[0][2jj+1]), pair 4 + jj = row 1
-                        double2* q0 = reinterpret_cast<double2*>(g4 + (size_t)jj * kBwdBlock * 2);
-                        double2* q1 = reinterpret_cast<double2*>(g4 + (size_t)(4 + jj) * kBwdBlock * 2);
-                        double2 a0 = *q0, a1 = *q1;
-                        a0.x = fma(o0, ha, a0.x); a0.y = fma(o0, hb, a0.y);
-                        a1.x = fma(o1, ha, a1.x); a1.y = fma(o1, hb, a1.y);
-                        *q0 = a0; *q1 = a1;
-                    }
-                    d2[2 * jj] = fma(c_mc.W4[1][2 * jj], o1, c_mc.W4[0][2 * jj] * o0) * fma(-ha, ha, 1.0);
-                    d2[2 * jj + 1] = fma(c_mc.W4[1][2 * jj + 1], o1, c_mc.W4[0][2 * jj + 1] * o0) * fma(-hb, hb, 1.0);
+                    g[kOffW4 + 2 * jj] = fma(o0, ha, g[kOffW4 + 2 * jj]); g[kOffW4 + 2 * jj + 1] = fma(o0, hb, g[kOffW4 + 2 * jj + 1]);
+                    g[kOffW4 + 8 + 2 * jj] = fma(o1, ha, g[kOffW4 + 8 + 2 * jj]); g[kOffW4 + 8 + 2 * jj + 1] = fma(o1, hb, g[kOffW4 + 8 + 2 * jj + 1]);
                 }
-                // layer 2: dW2 += delta2 (x) h0 ; delta0 = (1 - h0^2) . W2^T delta2   (h0 streamed pair by pair)
-                double d0[8];
+            }
+            {   // dW2 += d2 (x) h0   (h0 held, d2 streamed pair by pair)
+                double h0[8];
+#pragma unroll
+                for (int kk = 0; kk < 4; kk++) rec.load2(kk, h0[2 * kk], h0[2 * kk + 1]);
+#pragma unroll
+                for (int jj = 0; jj < 4; jj++) {
+                    double da, db;
+                    ops.load2(3 + jj, da, db);
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        g[kOffW2 + (2 * jj) * 8 + k] = fma(da, h0[k], g[kOffW2 + (2 * jj) * 8 + k]);
+                        g[kOffW2 + (2 * jj + 1) * 8 + k] = fma(db, h0[k], g[kOffW2 + (2 * jj + 1) * 8 + k]);
+                    }
+                }
+            }
+            {   // dW0 += d0 (x) (s1, s2, s3)
+                double s1, s2, s3, pad;
+                ops.load2(1, s1, s2);
+                ops.load2(2, s3, pad);
 #pragma unroll
                 for (int kk = 0; kk < 4; kk++) {
-                    double ha, hb;
-                    rec.load2(kk, ha, hb);
-                    double sa = c_mc.W2[0][2 * kk] * d2[0], sb = c_mc.W2[0][2 * kk + 1] * d2[0];
-                    g[kOffW2 + 2 * kk] = fma(d2[0], ha, g[kOffW2 + 2 * kk]); g[kOffW2 + 2 * kk + 1] = fma(d2[0], hb, g[kOffW2 + 2 * kk + 1]);
-#pragma unroll
-                    for (int jx = 1; jx < 8; jx++) {
-                        sa = fma(c_mc.W2[jx][2 * kk], d2[jx], sa); sb = fma(c_mc.W2[jx][2 * kk + 1], d2[jx], sb);
-                        g[kOffW2 + jx * 8 + 2 * kk] = fma(d2[jx], ha, g[kOffW2 + jx * 8 + 2 * kk]);
-                        g[kOffW2 + jx * 8 + 2 * kk + 1] = fma(d2[jx], hb, g[kOffW2 + jx * 8 + 2 * kk + 1]);
-                    }
-                    d0[2 * kk] = sa * fma(-ha, ha, 1.0);
-                    d0[2 * kk + 1] = sb * fma(-hb, hb, 1.0);
-                }
-                // layer 0: dW0 += delta0 (x) (s1, s2, s3)
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    g[kOffW0 + k * 3 + 0] = fma(d0[k], s1, g[kOffW0 + k * 3 + 0]);
-                    g[kOffW0 + k * 3 + 1] = fma(d0[k], s2, g[kOffW0 + k * 3 + 1]);
-                    g[kOffW0 + k * 3 + 2] = fma(d0[k], s3, g[kOffW0 + k * 3 + 2]);
+                    double da, db;
+                    ops.load2(7 + kk, da, db);
+                    g[kOffW0 + (2 * kk) * 3 + 0] = fma(da, s1, g[kOffW0 + (2 * kk) * 3 + 0]);
+                    g[kOffW0 + (2 * kk) * 3 + 1] = fma(da, s2, g[kOffW0 + (2 * kk) * 3 + 1]);
+                    g[kOffW0 + (2 * kk) * 3 + 2] = fma(da, s3, g[kOffW0 + (2 * kk) * 3 + 2]);
+                    g[kOffW0 + (2 * kk + 1) * 3 + 0] = fma(db, s1, g[kOffW0 + (2 * kk + 1) * 3 + 0]);
+                    g[kOffW0 + (2 * kk + 1) * 3 + 1] = fma(db, s2, g[kOffW0 + (2 * kk + 1) * 3 + 1]);
+                    g[kOffW0 + (2 * kk + 1) * 3 + 2] = fma(db, s3, g[kOffW0 + (2 * kk + 1) * 3 + 2]);
                 }
             }
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
 #pragma unroll
-        for (int k = 0; k < kOffW4; k++) {
+        for (int k = 0; k < kNumLive; k++) {
             const double v = Group<1>::sum(g[k]);
             if (writer) a.gps[(size_t)k * a.N + n] = v;
-        }
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const double2 p = *reinterpret_cast<const double2*>(g4 + (size_t)i * kBwdBlock * 2);
-            const int k0 = kOffW4 + (i < 4 ? 2 * i : 8 + 2 * (i - 4));
-            const double vx = Group<1>::sum(p.x), vy = Group<1>::sum(p.y);
-            if (writer) { a.gps[(size_t)k0 * a.N + n] = vx; a.gps[(size_t)(k0 + 1) * a.N + n] = vy; }
         }
     }
 }

@@ -297,34 +297,63 @@ template <int BLOCK> struct ActInSmem {
     }
     __device__ __forceinline__ ActInSmem wheel(int) const { return *this; }
 };
-// ---- reverse kernel, split tire adjoint (rollout_bwd2_kernel) ---------------------------------------------------------
-// Consumer -> producer: per lane and stage the xy-net Jacobian, the gated z derivative and the terrain gradient
-// (kJLen doubles as four 16-byte pairs: jxx jyx | jxy jyy | dzg - | dax day), formed one stage AHEAD of the producer.
-// Producer -> consumer: Fx_bar Fy_bar s1 s2 s3 (kFLen columns).  Both rings are kRing deep (slot q = stage mod kRing).
-// Named barriers: kBarFull + q = "F of a slot-q stage is staged" (producer arrives, consumer syncs),
-//                 kBarEmpty + q = "J of a slot-q stage is ready" (consumer arrives, producer syncs).  Because the consumer
-// publishes J of stage i+1 only after it has consumed F of stage i-1, and the producer stages F of stage i only after it has
-// read J of stage i, those two hand-shakes also protect the reuse of both rings.
-constexpr int kJLen = 8, kFLen = 5;
-template <int BLOCK> struct JInSmem {
-    const double* ring0;  // pair 0 of this lane in J buffer 0
+// ---- reverse kernel (rollout_bwd2_kernel): hand-over between the producer warp and the consumer warp ----------------------
+// The consumer owns the activation-record stream (a cp.async ring of kRing warp tiles, stage j in tile j mod kRing) and runs
+// kRing - 2 stages AHEAD of the producer with it.  The producer reads the activations of its stage straight from that tile,
+// runs the layered back-propagation of the tire network on its state chain (ode_bwd_nn_p) and stages the operands of the
+// three weight-gradient outer products for the consumer: o0 o1 | s1 s2 | s3 - | d2[8] | d0[8] = kFLen doubles as eleven
+// 16-byte pairs, a ring kRing deep (slot q = stage mod kRing).
+// Named barriers: kBarEmpty + q = "the activation tile of a slot-q stage has landed" (consumer arrives, producer syncs),
+//                 kBarFull + q  = "the operands of a slot-q stage are staged" (producer arrives, consumer syncs).
+// Because the consumer refills the tile of stage i only after it has consumed the operands of stage i, and the producer stages
+// them only after it has read the tile, those two hand-shakes also protect the reuse of the tiles and of the operand ring.
+// (Until the end of round 2 the consumer formed the 2x2 Jacobian of the xy-net a stage ahead and the producer used that; see
+// ode_bwd_nn_p in avs_model.cuh for why the layered pass on the state chain is cheaper.)
+// AVS_BWD_SWAP: the CTAs that land on the upper four warp slots of an SM swap the roles of their two warps, so that every
+// scheduler serves one producer and one consumer; the producer's lane index is then threadIdx.x & 31.
+#ifndef AVS_BWD_SWAP
+#define AVS_BWD_SWAP 1
+#endif
+#if AVS_BWD_SWAP
+#define AVS_BWD_LANE (threadIdx.x & 31)
+#else
+#define AVS_BWD_LANE threadIdx.x
+#endif
+constexpr int kFLen = 22;
+template <int TERR, int BLOCK> struct TInSmem {
+    const double* tile0;  // pair 0 of this lane in activation tile 0
     int count;
-    __device__ __forceinline__ void get(int, TireJac& J, double& dzg, double& dax, double& day) const {
+    __device__ __forceinline__ void get(int, double h0[8], double h2[8], double& dzg, double& dax, double& day) const {
         const int q = count & (kRing - 1);
         bar_sync64(kBarEmpty + q);
-        const double* b = ring0 + (size_t)q * kJLen * BLOCK;
-        const double2 p0 = *reinterpret_cast<const double2*>(b), p1 = *reinterpret_cast<const double2*>(b + 2 * BLOCK),
-                      p2 = *reinterpret_cast<const double2*>(b + 4 * BLOCK), p3 = *reinterpret_cast<const double2*>(b + 6 * BLOCK);
-        J.jxx = p0.x; J.jyx = p0.y; J.jxy = p1.x; J.jyy = p1.y; dzg = p2.x; dax = p3.x; day = p3.y;
+        const double* b = tile0 + (size_t)q * kActLen * BLOCK;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const double2 u = *reinterpret_cast<const double2*>(b + (size_t)i * 2 * BLOCK), v = *reinterpret_cast<const double2*>(b + (size_t)(4 + i) * 2 * BLOCK);
+            h0[2 * i] = u.x; h0[2 * i + 1] = u.y; h2[2 * i] = v.x; h2[2 * i + 1] = v.y;
+        }
+        dzg = *(b + (size_t)8 * 2 * BLOCK);
+        dax = 0.0; day = 0.0;
+        if (TERR != TERR_FLAT) {  // flat: the pair is neither stored nor fetched
+            const double2 g = *reinterpret_cast<const double2*>(b + (size_t)9 * 2 * BLOCK);
+            dax = g.x; day = g.y;
+        }
     }
 };
 template <int BLOCK> struct FOutSmem {
-    double* ring0;  // column 0 of this lane in F buffer 0
+    double* ring0;  // pair 0 of this lane in operand slot 0
     int count;
-    __device__ __forceinline__ void put(int, double fxb, double fyb, double s1, double s2, double s3) const {
+    __device__ __forceinline__ void put(int, double o0, double o1, double s1, double s2, double s3, const double d2[8], const double d0[8], const double*, const double*) const {
         const int q = count & (kRing - 1);
         double* dst = ring0 + (size_t)q * kFLen * BLOCK;
-        dst[0] = fxb; dst[BLOCK] = fyb; dst[2 * BLOCK] = s1; dst[3 * BLOCK] = s2; dst[4 * BLOCK] = s3;
+        *reinterpret_cast<double2*>(dst) = make_double2(o0, o1);
+        *reinterpret_cast<double2*>(dst + 2 * BLOCK) = make_double2(s1, s2);
+        *reinterpret_cast<double2*>(dst + 4 * BLOCK) = make_double2(s3, 0.0);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            *reinterpret_cast<double2*>(dst + (size_t)(3 + i) * 2 * BLOCK) = make_double2(d2[2 * i], d2[2 * i + 1]);
+            *reinterpret_cast<double2*>(dst + (size_t)(7 + i) * 2 * BLOCK) = make_double2(d0[2 * i], d0[2 * i + 1]);
+        }
         bar_arrive64(kBarFull + q);
     }
 };
@@ -344,12 +373,12 @@ __device__ __forceinline__ void ode_bwd_call2(int lane0, int voff, int slotXS, i
     // LDS.128 / STS.128 of the warp instead of four, and a four times shorter store drain before the callee returns
     const RecCol XS = rec_col<BLOCK>(slotXS, voff);
     const RecCol LAM = rec_col<BLOCK>(slotLAM, voff), YB = LAM.sub(13), KB = LAM.sub(26);
-    JInSmem<BLOCK> jin{g_smem + (size_t)slotJ * BLOCK + (size_t)threadIdx.x * 2, stage_count};
-    FOutSmem<BLOCK> fout{g_smem + (size_t)slotF * BLOCK + threadIdx.x, stage_count};
+    TInSmem<TERR, BLOCK> tin{g_smem + (size_t)slotJ * BLOCK + (size_t)AVS_BWD_LANE * 2, stage_count};
+    FOutSmem<BLOCK> fout{g_smem + (size_t)slotF * BLOCK + (size_t)AVS_BWD_LANE * 2, stage_count};
     double X[14], kb[14], Xb[14];
 #pragma unroll
     for (int i = 0; i < 7; i++) { XS.load2(i, X[2 * i], X[2 * i + 1]); KB.load2(i, kb[2 * i], kb[2 * i + 1]); }
-    ode_bwd_nn_j<1, TERR>(c_mc, lane0, X, ul, ur, kb, Xb, jin, fout);
+    ode_bwd_nn_p<1, TERR>(c_mc, lane0, X, ul, ur, kb, Xb, tin, fout);
     // rk4_bwd_stage_update on pairs
     Xb[13] = 0.0;
     const double h = kDt;

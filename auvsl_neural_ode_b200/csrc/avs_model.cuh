@@ -1275,6 +1275,122 @@ AVS_HD void ode_bwd_nn_j(const ModelConst& mc, int lane0, const double X[13], do
     }
     quat_to_R_bwd(X, Rb, Xb);
 }
+// The same adjoint with the LAYERED back-propagation of the tire network run right here, on the state chain (reverse kernel,
+// end of round 2): `tin.get(k, h0, h2, dzg, dax, day)` delivers the stored activations of this thread's k-th wheel,
+// `fout.put(k, o0, o1, s1, s2, s3, d2, d0)` hands over the operands of the three weight-gradient outer products
+//   dW4 += (o0, o1) (x) h2 ,  dW2 += d2 (x) h0 ,  dW0 += d0 (x) (s1, s2, s3).
+// Arithmetic and order are those of tire_nn_bwd, so the result is bit-identical to ode_bwd_nn.  Why not the Jacobian split
+// above: both rollout kernels turned out to be bound by issue slots (an FP64 instruction takes two, any other one; measured
+// by moving the 2x2 Jacobian's ~216 FP64 instructions per stage into the forward kernel: it got slower by exactly their issue
+// time wherever they were placed), and forming J on top of the layered pass costs ~210 FP64 instructions per wheel and stage
+// more than the layered pass alone, which yields (vx_bar, vy_bar) as a by-product (16 more FMAs).
+#ifndef AVS_BWD_EARLY_GET
+#define AVS_BWD_EARLY_GET 1
+#endif
+template <int WPT, int TERR, class XD, class TIn, class FOut>
+AVS_HD void ode_bwd_nn_p(const ModelConst& mc, int lane0, const double X[13], double ul, double ur, const XD& Xdb, double Xb[13], TIn& tin, FOut& fout) {
+    double Sb[6];
+    base_bwd_S(mc, Xdb, Sb);
+    double gx[3] = {0, 0, 0}, gy[3] = {0, 0, 0}, gs[3] = {0, 0, 0};  // sum sx*cpb, sum sy*cpb, sum cpb
+    double wb[3] = {0, 0, 0}, vb[3] = {0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < WPT; k++) {
+        const int i = lane0 + k;
+        double tx, ty;
+        wheel_sign(i, tx, ty);
+        const double qd = (i & 1) ? ur : ul;
+        double Fb[3];
+        WheelAct act;
+#if AVS_BWD_EARLY_GET
+        double h0[8], h2[8], dzg, dax, day;
+        tin.get(k, h0, h2, dzg, dax, day);  // first: the wait for the tile and the loads overlap the head of the stage
+#endif
+        const double cvx = X[10] + (X[8] * kRz - X[9] * ty), cvy = X[11] + (X[9] * tx - X[7] * kRz);
+        const double s1 = (qd * kTireRadius - cvx) * (1.0 / kInStd1), s2 = qd * (1.0 / kInStd2), s3 = cvy * (1.0 / kInStd3);
+        wheel_aba_act(tx, ty, X, qd, act);
+        wheel_aba_bwd(tx, ty, qd, act, Sb, Fb, wb, vb);
+#if !AVS_BWD_EARLY_GET
+        double h0[8], h2[8], dzg, dax, day;
+        tin.get(k, h0, h2, dzg, dax, day);
+#endif
+        const double o0 = Fb[0] * kOutStd0, o1 = Fb[1] * kOutStd1;
+        double d2[8], d0[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) d2[q] = fma(mc.W4[1][q], o1, mc.W4[0][q] * o0);
+#pragma unroll
+        for (int q = 0; q < 8; q++) d2[q] *= fma(-h2[q], h2[q], 1.0);
+#pragma unroll
+        for (int q = 0; q < 8; q++) d0[q] = mc.W2[0][q] * d2[0];
+#pragma unroll
+        for (int j = 1; j < 8; j++) {
+#pragma unroll
+            for (int q = 0; q < 8; q++) d0[q] = fma(mc.W2[j][q], d2[j], d0[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++) d0[q] *= fma(-h0[q], h0[q], 1.0);
+        fout.put(k, o0, o1, s1, s2, s3, d2, d0, h0, h2);
+        double s1a = mc.W0[0][0] * d0[0], s1b = mc.W0[1][0] * d0[1];
+        double s3a = mc.W0[0][2] * d0[0], s3b = mc.W0[1][2] * d0[1];
+#pragma unroll
+        for (int j = 2; j < 8; j += 2) {
+            s1a = fma(mc.W0[j][0], d0[j], s1a); s1b = fma(mc.W0[j + 1][0], d0[j + 1], s1b);
+            s3a = fma(mc.W0[j][2], d0[j], s3a); s3b = fma(mc.W0[j + 1][2], d0[j + 1], s3b);
+        }
+        double cvb[3];
+        cvb[0] = -(s1a + s1b) * (1.0 / kInStd1);
+        cvb[1] = (s3a + s3b) * (1.0 / kInStd3);
+        cvb[2] = kNNDamp * Fb[2];
+        const double sinkb = (Fb[2] * kOutStd2 * dzg) * (1.0 / kInStd0);
+        // cv = v + w x r
+        vb[0] += cvb[0]; vb[1] += cvb[1]; vb[2] += cvb[2];
+        wb[0] += ty * cvb[2] - kRz * cvb[1];
+        wb[1] += kRz * cvb[0] - tx * cvb[2];
+        wb[2] += tx * cvb[1] - ty * cvb[0];
+        // sink = alt(cpx, cpy) - cpz
+        const double cpb0 = (TERR == TERR_FLAT) ? 0.0 : sinkb * dax, cpb1 = (TERR == TERR_FLAT) ? 0.0 : sinkb * day, cpb2 = -sinkb;
+        const double sx = (i & 2) ? -1.0 : 1.0, sy = (i & 1) ? -1.0 : 1.0;
+        gx[0] += sx * cpb0; gx[1] += sx * cpb1; gx[2] += sx * cpb2;
+        gy[0] += sy * cpb0; gy[1] += sy * cpb1; gy[2] += sy * cpb2;
+        gs[0] += cpb0; gs[1] += cpb1; gs[2] += cpb2;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        if (!(TERR == TERR_FLAT && c < 2)) { gx[c] = Group<WPT>::sum(gx[c]); gy[c] = Group<WPT>::sum(gy[c]); gs[c] = Group<WPT>::sum(gs[c]); }
+        wb[c] = Group<WPT>::sum(wb[c]); vb[c] = Group<WPT>::sum(vb[c]);
+    }
+    double R[9], Rb[9];
+    quat_to_R(X, R);
+    base_bwd_rest(R, X, Xdb, Sb, Xb, Rb);
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        Rb[3 * c + 0] = fma(kTx, gx[c], Rb[3 * c + 0]);
+        Rb[3 * c + 1] = fma(kTy, gy[c], Rb[3 * c + 1]);
+        Rb[3 * c + 2] = fma(kRz, gs[c], Rb[3 * c + 2]);
+        Xb[4 + c] += gs[c];
+        Xb[7 + c] += wb[c];
+        Xb[10 + c] += vb[c];
+    }
+    quat_to_R_bwd(X, Rb, Xb);
+}
+// host-side provider for ode_bwd_nn_p: activations from four consecutive records, weight gradient applied at once
+template <class Acc> struct LayeredFromRecords {
+    const double* act; Acc& acc;
+    AVS_HD void get(int k, double h0[8], double h2[8], double& dzg, double& dax, double& day) {
+        NNAct a;
+        act_load(a, dax, day, ActInPtr{act + (size_t)k * kActLen});
+        dzg = a.dz4;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { h0[i] = a.h0[i]; h2[i] = a.h2[i]; }
+    }
+    AVS_HD void put(int, double o0, double o1, double s1, double s2, double s3, const double d2[8], const double d0[8], const double h0[8], const double h2[8]) {
+        double op[kGradOps];
+        op[0] = o0; op[1] = o1;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { op[2 + i] = h2[i]; op[10 + i] = d2[i]; op[18 + i] = h0[i]; op[26 + i] = d0[i]; }
+        op[34] = s1; op[35] = s2; op[36] = s3;
+        acc.record(op);
+    }
+};
 // host-side (and reference) providers: Jacobian formed on the spot from the activation records, weight gradient applied at once
 template <class Acc> struct JFromRecords {
     const ModelConst& mc; const double* act; Acc& acc;  // act = four consecutive kActLen-double records

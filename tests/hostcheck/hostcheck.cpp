@@ -217,6 +217,23 @@ void hc_ode_vjp_split(const hc_model* m, const double* X13, const double* u2, co
     }
     memcpy(gW104, acc.g, sizeof(acc.g));
 }
+// the same product through ode_bwd_nn_p (layered back-propagation on the state chain, outer-product operands handed over):
+// what the reverse kernel's producer warp runs
+void hc_ode_vjp_layered(const hc_model* m, const double* X13, const double* u2, const double* Xdb13, double* Xb13, double* gW104) {
+    ModelConst mc; mk(m, mc);
+    HostAcc acc;
+    double kb[13], Xd[13], actrec[kActLen * 4];
+    memcpy(kb, Xdb13, sizeof(kb));
+    Scratch<1> KB{kb};
+    LayeredFromRecords<HostAcc> io{actrec, acc};
+    switch (m->terr) {
+        case 0: ode_fwd<4, 0, 0, true>(mc, 0, X13, u2[0], u2[1], Xd, nullptr, ActOutPtr{actrec}); ode_bwd_nn_p<4, 0>(mc, 0, X13, u2[0], u2[1], KB, Xb13, io, io); break;
+        case 1: ode_fwd<4, 0, 1, true>(mc, 0, X13, u2[0], u2[1], Xd, nullptr, ActOutPtr{actrec}); ode_bwd_nn_p<4, 1>(mc, 0, X13, u2[0], u2[1], KB, Xb13, io, io); break;
+        case 2: ode_fwd<4, 0, 2, true>(mc, 0, X13, u2[0], u2[1], Xd, nullptr, ActOutPtr{actrec}); ode_bwd_nn_p<4, 2>(mc, 0, X13, u2[0], u2[1], KB, Xb13, io, io); break;
+        default: ode_fwd<4, 0, 3, true>(mc, 0, X13, u2[0], u2[1], Xd, nullptr, ActOutPtr{actrec}); ode_bwd_nn_p<4, 3>(mc, 0, X13, u2[0], u2[1], KB, Xb13, io, io); break;
+    }
+    memcpy(gW104, acc.g, sizeof(acc.g));
+}
 // SoA batch rollout, same buffers as the kernels
 void hc_rollout(const hc_model* m, int N, int T, int substeps, const double* x0, const double* ctrl, double* x_list, double* x_final) {
     ModelConst mc; mk(m, mc);

@@ -116,6 +116,13 @@ def ode_vjp(m, X13, u, Xdb):
     return xb, g
 
 
+def ode_vjp_layered(m, X13, u, Xdb):
+    X13, u, Xdb = _f64(X13), _f64(u), _f64(Xdb)
+    xb, g = np.zeros(13), np.zeros(104)
+    lib().hc_ode_vjp_layered(C.byref(m), _p(X13), _p(u), _p(Xdb), _p(xb), _p(g))
+    return xb, g
+
+
 def ode_vjp_split(m, X13, u, Xdb):
     X13, u, Xdb = _f64(X13), _f64(u), _f64(Xdb)
     xb, g = np.zeros(13), np.zeros(104)

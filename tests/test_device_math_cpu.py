@@ -241,6 +241,11 @@ def test_split_tire_adjoint_matches_layered_adjoint():
             xb2, gW2 = hc.ode_vjp_split(m, X, u, lam)
             np.testing.assert_allclose(xb2, xb, rtol=0, atol=1e-14 * np.abs(xb).max())
             np.testing.assert_array_equal(gW2, gW)
+            # what the reverse kernel's producer warp runs since the end of round 2 (ode_bwd_nn_p: the layered pass on the state
+            # chain, outer-product operands handed to the consumer warp): the one-piece adjoint's arithmetic in the same order
+            xb3, gW3 = hc.ode_vjp_layered(m, X, u, lam)
+            np.testing.assert_array_equal(xb3, xb)
+            np.testing.assert_array_equal(gW3, gW)
 
 
 def test_contact_search_matches_oracle():
