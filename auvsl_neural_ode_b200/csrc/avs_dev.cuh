@@ -192,41 +192,38 @@ __device__ __noinline__ void ode_fwd_stage_call_tiles(int tid, int lane0, double
     double x[14], k[13];
 #pragma unroll
     for (int i = 0; i < 7; i++) { const double2 v = *reinterpret_cast<const double2*>(Tt + i * kCkPairStride); x[2 * i] = v.x; x[2 * i + 1] = v.y; }
-    if (STORE && rec_tile) {  // warp-uniform
+    if (STORE) {  // every warp of the launch owns a tile (ck_rec_stride pads the records to whole CTAs): no branch
         const int l = tid & 31;
         const double* src = wbase + 2 * kCkTile + l * 2;
         *reinterpret_cast<double2*>(rec_tile + l * 2) = *reinterpret_cast<const double2*>(src);
         if (l < kCkTile / 2 - 32) *reinterpret_cast<double2*>(rec_tile + 64 + l * 2) = *reinterpret_cast<const double2*>(src + 64);
     }
+    // X and ACC are fetched BEFORE the ODE evaluation (their 28 registers stay live across it; the 2-CTA build has the room), so
+    // that the stage update at the tail does not start with a shared-memory round trip (10.21 -> 10.13 ms)
+    double X[14], acc[14];
+#pragma unroll
+    for (int i = 0; i < 7; i++) { const double2 v = *reinterpret_cast<const double2*>(Xt + i * kCkPairStride); X[2 * i] = v.x; X[2 * i + 1] = v.y; }
+    if (s > 0) {
+#pragma unroll
+        for (int i = 0; i < 7; i++) { const double2 v = *reinterpret_cast<const double2*>(At + i * kCkPairStride); acc[2 * i] = v.x; acc[2 * i + 1] = v.y; }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 14; c++) acc[c] = 0.0;
+    }
     ode_fwd<1, TIRE_NN, TERR, STORE>(c_mc, lane0, x, ul, ur, k, nullptr, ActOutPtr{act, kActPairStride});
     const double h = kDt;
     double inv;
-    double X[14];
-#pragma unroll
-    for (int i = 0; i < 7; i++) { const double2 v = *reinterpret_cast<const double2*>(Xt + i * kCkPairStride); X[2 * i] = v.x; X[2 * i + 1] = v.y; }
     if (s < 3) {
         const double wgt = (s == 0) ? 1.0 : 2.0;   // k1 + 2 k2 + 2 k3 + k4
         const double cs = (s == 2) ? h : .5 * h;   // X + .5h k1, X + .5h k2, X + h k3
-        double acc[14];
-        acc[13] = 0.0;
-        if (s == 0) {
 #pragma unroll
-            for (int c = 0; c < 13; c++) acc[c] = fma(wgt, k[c], 0.0);
-        } else {
-#pragma unroll
-            for (int i = 0; i < 7; i++) { const double2 v = *reinterpret_cast<const double2*>(At + i * kCkPairStride); acc[2 * i] = v.x; acc[2 * i + 1] = v.y; }
-#pragma unroll
-            for (int c = 0; c < 13; c++) acc[c] = fma(wgt, k[c], acc[c]);
-        }
+        for (int c = 0; c < 13; c++) acc[c] = fma(wgt, k[c], acc[c]);
 #pragma unroll
         for (int i = 0; i < 7; i++) *reinterpret_cast<double2*>(At + i * kCkPairStride) = make_double2(acc[2 * i], acc[2 * i + 1]);
 #pragma unroll
         for (int c = 0; c < 13; c++) x[c] = fma(cs, k[c], X[c]);
         renorm(x, inv);
     } else {
-        double acc[14];
-#pragma unroll
-        for (int i = 0; i < 7; i++) { const double2 v = *reinterpret_cast<const double2*>(At + i * kCkPairStride); acc[2 * i] = v.x; acc[2 * i + 1] = v.y; }
 #pragma unroll
         for (int c = 0; c < 13; c++) x[c] = fma(h / 6.0, fma(1.0, k[c], acc[c]), X[c]);
         renorm(x, inv);
@@ -248,8 +245,7 @@ template <int TERR, int BLOCK, bool STORE> struct FusedStepTiles {
         const size_t NK = (size_t)a.Nc;
         const size_t rec_stride = ck_rec_stride(NK);
         const size_t gidx = (size_t)blockIdx.x * BLOCK + threadIdx.x;
-        const bool warp_valid = (gidx >> 5) * kCkTileVeh < NK;  // the warp's first vehicle exists: its state tile does
-        double* rec = (STORE && warp_valid) ? a.ckpt + (step * 4) * rec_stride + (gidx >> 5) * kCkTile : nullptr;
+        double* rec = STORE ? a.ckpt + (step * 4) * rec_stride + (gidx >> 5) * kCkTile : nullptr;  // every warp of the launch owns a tile
         const size_t act_stride = act_stage_doubles(NK);
         double* act = STORE ? a.act + (step * 4) * act_stride + act_lane_offset(gidx) : nullptr;
         const int tid = (int)threadIdx.x;

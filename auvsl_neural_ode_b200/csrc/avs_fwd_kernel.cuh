@@ -4,6 +4,8 @@
 
 namespace avs {
 
+static_assert(kFwdBlock <= 4 * 4 * kCkTileVeh, "ck_rec_stride pads the state records to 32 vehicles: a forward CTA must not span more");
+
 // __launch_bounds__(.., 3): the register cap of three resident CTAs (170) is what makes ptxas pick the wide schedule for the
 // non-inlined stage callee (163-168 registers, 1 % back-to-back dependent FP64); without it ptxas settles on 128 registers and a
 // more serial order (measured: forward+store 14.1 ms vs 11.5 ms at N = 4096 x T = 200).

@@ -508,11 +508,15 @@ AVS_HD double ztab_eval(const double* tab, double s0) {
     const double b0 = fma(a1, y2, a0), b1 = fma(a3, y2, a2);
     return fma(a4, y8, fma(b1, y4, b0));
 }
-// value AND derivative (d z4 / d s0) for s0 > 0, by one joint Horner pass over the value coefficients — the form the STORE
-// instantiation of the forward kernel keeps: it runs at its register cap, and there the short dependent chain with ten 8-byte
-// coefficient loads schedules better than Estrin's scheme with 16-byte loads (measured, round 2: 11.08 against 11.3-11.9 ms)
+// value AND derivative (d z4 / d s0), by one joint Horner pass over the value coefficients — the form the STORE instantiation
+// of the forward kernel uses (18 FP64 instructions; Estrin's scheme for both would take 24, and the kernel is bound by issue
+// slots).  Branch-free since the end of round 2 (forward + store 10.48 -> 10.23 ms); under the 170-register cap of the earlier
+// three-CTA build every branch-free variant had been slower (11.3-11.9 against 11.08 ms).
 AVS_HD double ztab_eval_d(const double* tab, double s0, double& dz) {
-    const double sc = s0 < kZTabSMax ? s0 : kZTabSMax;
+    // evaluated at max(s0, 0), the caller gates value and derivative by selects: no divergent region, so ptxas interleaves the
+    // Horner chain (18 dependent FMAs, ~150 cycles when it ran alone inside `s0 > 0 ? ... : 0`: ncu source page) with the xy-net
+    const double sp = s0 > 0.0 ? s0 : 0.0;
+    const double sc = sp < kZTabSMax ? sp : kZTabSMax;
     const double u = sc * (double)kZTabPerUnit;
     int i = (int)u;
     i = i > kZTabN - 1 ? kZTabN - 1 : i;
@@ -520,7 +524,7 @@ AVS_HD double ztab_eval_d(const double* tab, double s0, double& dz) {
     const double* c = tab + (size_t)i * kZTabRow;
     double cc[kZTabDeg + 1];
 #pragma unroll
-    for (int k = 0; k <= kZTabDeg; k++) {
+    for (int k = 0; k <= kZTabDeg; k++) {  // ten 8-byte loads: five 16-byte ones were measured slower here (10.29 against 10.21 ms)
 #if defined(__CUDA_ARCH__)
         cc[k] = __ldg(c + k);
 #else
@@ -593,7 +597,10 @@ AVS_HD void tire_nn_fwd(const ModelConst& mc, double vx, double vy, double w, do
     a.dz4 = 0.0;
     double z4;
     if (WANT_D) {
-        z4 = s0 > 0.0 ? ztab_eval_d(mc.ztab, s0, a.dz4) : 0.0;
+        double dz;
+        const double zt = ztab_eval_d(mc.ztab, s0, dz);
+        z4 = s0 > 0.0 ? zt : 0.0;
+        a.dz4 = s0 > 0.0 ? dz : 0.0;
     } else {
         const double zt = ztab_eval(mc.ztab, s0);  // branch-free: evaluated at max(s0, 0)
         z4 = s0 > 0.0 ? zt : 0.0;

@@ -71,7 +71,9 @@ AVS_HD double ld(const double* p) {
 constexpr int kCkRows = 14;  // 13 live states + 1 inverse norm per stage record
 // state tiles: the records of 8 consecutive vehicles (one warp of either rollout kernel), pair-major
 constexpr int kCkTileVeh = 8, kCkPairStride = 2 * kCkTileVeh, kCkTile = kCkRows * kCkTileVeh;  // 16 / 112 doubles
-AVS_HD size_t ck_rec_stride(size_t nc) { return ((nc + kCkTileVeh - 1) / kCkTileVeh) * kCkTile; }  // doubles between consecutive records
+// doubles between consecutive records: whole 128-thread CTAs of the forward kernel (4 tiles), so that every one of its warps owns a
+// tile and stores it unconditionally (no branch at the head of the stage callee, avs_dev.cuh)
+AVS_HD size_t ck_rec_stride(size_t nc) { return ((nc + 4 * kCkTileVeh - 1) / (4 * kCkTileVeh)) * 4 * kCkTile; }
 AVS_HD size_t ck_lane_offset(size_t n) { return (n / kCkTileVeh) * kCkTile + (n % kCkTileVeh) * 2; }  // pair 0 of vehicle n inside a record
 // element c of the record whose pair 0 is at p
 AVS_HD size_t ck_elem(int c) { return (size_t)(c >> 1) * kCkPairStride + (c & 1); }
