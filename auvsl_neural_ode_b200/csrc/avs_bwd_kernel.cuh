@@ -7,11 +7,12 @@
 // writes gps[104][N], the producer writes loss[N].
 //
 //   rollout_bwd2_kernel:
-//     * producer — state-tile stream (two contiguous cp.async one stage ahead), adjoint of the base link, the ABA wheel passes,
+//     * producer — adjoint of the base link, the ABA wheel passes,
 //       contact geometry / terrain gradient, quaternion normalisations AND the layered back-propagation of the tire network
 //       (ode_bwd_nn_p), inlined into the stage loop; it reads the activations from the consumer's tile of the stage and stages
 //       the 21 operands of the weight-gradient outer products;
-//     * consumer — activation-record stream (own cp.async ring of kTiles tiles, kLook stages ahead of the producer) and the
+//     * consumer — BOTH record streams (cp.async rings of kTiles activation tiles and kSRing state tiles, kLook stages ahead of
+//       the producer, which neither issues nor waits for a copy) and the
 //       three outer products of the current stage into dL/dW: 104 accumulators per lane in registers.
 //   CTAs on the upper warp slots of an SM swap the roles of their warps, so that every scheduler serves one producer and one
 //   consumer (AVS_BWD_SWAP): both rollout kernels are bound by issue slots, and the two roles are unequal now.
@@ -26,10 +27,9 @@ namespace avs {
 
 constexpr int kBwdThreads = 2 * kBwdBlock;  // producer warp + consumer warp
 
-// shared memory, in columns of kBwdBlock doubles: adjoint tiles LAM | YB | KB (3 x kCkTile doubles) 0 | state tile A 11 |
-// state tile B 15 | activation tiles 19 (kTiles x kActLen columns) | operand ring (kRing x kFLen columns)
-constexpr int kB2SlotRecA = 11, kB2SlotRecB = 15, kB2SlotT = 19, kLook = kRing - 2, kTiles = kRing, kB2SlotF = kB2SlotT + kTiles * kActLen, kB2Slots = kB2SlotF + kRing * kFLen;
-
+// shared memory, in columns of kBwdBlock doubles: adjoint tiles LAM | YB | KB (3 x kCkTile doubles) 0 | state-tile ring 11
+// (kSRing x kSTileCols columns) | activation tiles (kTiles x kActLen columns) | operand ring (kRing x kFLen columns)
+constexpr int kB2SlotRec = 11, kB2SlotT = kB2SlotRec + kSRing * kSTileCols, kLook = kRing - 2, kTiles = kRing, kB2SlotF = kB2SlotT + kTiles * kActLen, kB2Slots = kB2SlotF + kRing * kFLen;
 template <int TERR>
 __global__ void __launch_bounds__(kBwdThreads) rollout_bwd2_kernel(const __grid_constant__ RolloutArgs a) {
     const int lane = threadIdx.x & 31;
@@ -60,13 +60,12 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd2_kernel(const __grid_
         int stage_counter = 0;
         const int voff = 2 * (n % kCkTileVeh);  // this lane's vehicle inside the CTA's state tile (tail lanes: the mirrored vehicle)
         auto mk_odeb = [lane0, voff, &stage_counter](double ul, double ur) {
-            return OdeBwdCall2<TERR, kBwdBlock>{lane0, voff, kB2SlotRecA, kB2SlotRecB, 0, kB2SlotT, kB2SlotF, ul, ur, &stage_counter};
+            return OdeBwdCall2<TERR, kBwdBlock>{lane0, voff, 0, kB2SlotT, kB2SlotF, ul, ur, &stage_counter};
         };
         static_assert(kBwdBlock == 4 * kCkTileVeh, "a reverse CTA serves exactly one state tile");
-        const size_t rstride = ck_rec_stride(a.Nc);
-        CkptStreamRec<kBwdBlock> st{a.ckpt + (size_t)nrec * rstride + (size_t)blockIdx.x * kCkTile, rstride, nrec, kB2SlotRecA, kB2SlotRecB, 0, voff, a.ckpt, a.ckpt_doubles};
-        st.init();
-        static_assert(3 * kCkTile <= kB2SlotRecA * kBwdBlock && kB2SlotRecA * kBwdBlock + kCkTile <= kB2SlotRecB * kBwdBlock && kB2SlotRecB * kBwdBlock + kCkTile <= kB2SlotT * kBwdBlock, "tile map");
+        static_assert(3 * kCkTile <= kB2SlotRec * kBwdBlock && kCkTile <= kSTileCols * kBwdBlock, "tile map");
+        CkptStreamRing<kBwdBlock> st{0, kB2SlotRec, voff};
+        bar_sync64(0);  // the consumer has fetched the final-state tile (and the tiles of the first stages)
         rollout_bwd_body(a, n, loss, rec_col<kBwdBlock>(0, voff), st, mk_odeb);
         if (writer) a.loss[n] = loss;
     } else {
@@ -79,7 +78,22 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd2_kernel(const __grid_
         double* const tiles = g_smem + (size_t)kB2SlotT * kBwdBlock + (size_t)lane * 2;
         const double* const fring = g_smem + (size_t)kB2SlotF * kBwdBlock + (size_t)lane * 2;
         auto tile_of = [tiles](int t) { return tiles + (size_t)t * kActLen * kBwdBlock; };
-        auto prefetch = [&](long j, int t) {  // activation record of reverse stage j -> tile t
+        // state tiles: record number k counted from the final state backwards -> slot k mod kSRing (CkptStreamRing, avs_dev.cuh);
+        // lanes 0..31 fetch the first 512 bytes of the 896-byte tile, lanes 0..23 the rest
+        const size_t rstride = ck_rec_stride(a.Nc);
+        const double* const rec_last = a.ckpt + (size_t)nrec * rstride + (size_t)blockIdx.x * kCkTile;
+        auto fetch_state = [&](long k) {
+            if (k <= nrec) {
+                const double* src = rec_last - (size_t)k * rstride;
+                AVS_DBG_RANGE("state tile (reverse prefetch)", src, kCkTile, a.ckpt, a.ckpt_doubles);
+                double* dst = g_smem + (size_t)(kB2SlotRec + (int)(k & (kSRing - 1)) * kSTileCols) * kBwdBlock;
+                const unsigned s0 = (unsigned)__cvta_generic_to_shared(dst + lane * 2);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0), "l"(src + lane * 2) : "memory");
+                if (lane < kCkTile / 2 - 32) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + 512u), "l"(src + 64 + lane * 2) : "memory");
+            }
+        };
+        auto prefetch = [&](long j, int t) {  // activation record of reverse stage j -> tile t, and the state tile that stage reads
+            fetch_state(j + 1);
             if (j < nrec) {
                 const double* src = act_last - (size_t)j * astride;
                 AVS_DBG_RANGE("activation record (reverse prefetch)", src, 9 * kActPairStride + 2, a.act, a.act_doubles);
@@ -97,16 +111,18 @@ __global__ void __launch_bounds__(kBwdThreads) rollout_bwd2_kernel(const __grid_
         // the tiles keep arriving.  Ring safety: the tile of stage i is refilled after the operands of stage i have been consumed,
         // and those are staged after the producer has read the tile.  Stage j lives in tile j mod kTiles (kTiles = kLook + 2 =
         // kRing, a power of two: no index registers).
+        fetch_state(0);
 #pragma unroll 1
         for (int i = 0; i <= kLook; i++) prefetch(i, i);
         asm volatile("cp.async.wait_group 0;" ::: "memory");
+        bar_sync64(0);  // final-state tile in place: the producer starts with the row loss at it
 #pragma unroll 1
         for (int i = 0; i < kLook; i++) if (i < nrec) bar_arrive64(kBarEmpty + i);
 #pragma unroll 1
         for (long j = 0; j < nrec; j++) {
             const int t0 = (int)(j & (kTiles - 1));
             prefetch(j + kLook + 1, (int)((j + kLook + 1) & (kTiles - 1)));
-            if (j + kLook < nrec) bar_arrive64(kBarEmpty + (int)((j + kLook) & (kRing - 1)));  // its tile landed before the last wait
+            if (j + kLook < nrec) bar_arrive64(kBarEmpty + (int)((j + kLook) & (kRing - 1)));  // its tiles landed before the last wait
             const int q = (int)(j & (kRing - 1));
             bar_sync64(kBarFull + q);
             const ActInSmem<kBwdBlock> rec{tile_of(t0)};

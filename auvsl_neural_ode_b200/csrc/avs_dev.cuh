@@ -320,8 +320,7 @@ template <int TERR, int BLOCK> struct TInSmem {
     const double* tile0;  // pair 0 of this lane in activation tile 0
     int count;
     __device__ __forceinline__ void get(int, double h0[8], double h2[8], double& dzg, double& dax, double& day) const {
-        const int q = count & (kRing - 1);
-        bar_sync64(kBarEmpty + q);
+        const int q = count & (kRing - 1);  // the stage head (ode_bwd_call2) has already waited for "the tiles of this stage have landed"
         const double* b = tile0 + (size_t)q * kActLen * BLOCK;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
@@ -362,13 +361,13 @@ template <int BLOCK> __device__ __forceinline__ RecCol rec_col(int slot, int vof
 // cost goes away: ~40-cycle instruction-fetch misses at the call and at the return, the S2R / CgaCtaId address prologue, and
 // the drain of the last STS.128 before RET (11.31 -> 10.91 ms).
 template <int TERR, int BLOCK>
-__device__ __forceinline__ void ode_bwd_call2(int lane0, int voff, int slotXS, int slotLAM, int slotJ, int slotF, double ul, double ur, int stage_count, int s) {
+__device__ __forceinline__ void ode_bwd_call2(int lane0, int voff, const RecCol XS, int slotLAM, int slotJ, int slotF, double ul, double ur, int stage_count, int s) {
     // XS = the staged state tile; the loop-carried adjoints LAM | YB | KB are vehicle-level 13-vectors, bit-identical in the four
     // lanes of a vehicle (the butterfly sums are commutative), so they live in three tiles of the same shape: the four lanes
     // store the same 16 bytes to the same address and read them back by broadcast — one shared-memory wavefront per
     // LDS.128 / STS.128 of the warp instead of four, and a four times shorter store drain before the callee returns
-    const RecCol XS = rec_col<BLOCK>(slotXS, voff);
     const RecCol LAM = rec_col<BLOCK>(slotLAM, voff), YB = LAM.sub(13), KB = LAM.sub(26);
+    bar_sync64(kBarEmpty + (stage_count & (kRing - 1)));  // the consumer's cp.async of this stage's state tile and activation tile have landed
     TInSmem<TERR, BLOCK> tin{g_smem + (size_t)slotJ * BLOCK + (size_t)AVS_BWD_LANE * 2, stage_count};
     FOutSmem<BLOCK> fout{g_smem + (size_t)slotF * BLOCK + (size_t)AVS_BWD_LANE * 2, stage_count};
     double X[14], kb[14], Xb[14];
@@ -400,53 +399,27 @@ __device__ __forceinline__ void ode_bwd_call2(int lane0, int voff, int slotXS, i
     }
 }
 template <int TERR, int BLOCK> struct OdeBwdCall2 {
-    int lane0, voff, slotXA, slotXB, slotLAM, slotJ, slotF;
+    int lane0, voff, slotLAM, slotJ, slotF;
     double ul, ur;
     int* stage_counter;
     template <class V> __device__ __forceinline__ void operator()(RecCol XS, V, V, V, int s, const double*) const {
-        const bool isA = XS.base == rec_col<BLOCK>(slotXA, voff).base;
-        ode_bwd_call2<TERR, BLOCK>(lane0, voff, isA ? slotXA : slotXB, slotLAM, slotJ, slotF, ul, ur, (*stage_counter)++, s);
+        ode_bwd_call2<TERR, BLOCK>(lane0, voff, XS, slotLAM, slotJ, slotF, ul, ur, (*stage_counter)++, s);
     }
 };
-// state-record stream only (the producer of the split kernel never touches the activation records).  One record of the
-// warp's 8 vehicles = one contiguous kCkTile-double state tile: lanes 0..31 fetch its first 512 bytes, lanes 0..23 the other
-// 384 (two coalesced cp.async instead of seven 16-byte gathers per lane that cost 32 shared-memory wavefronts each); every
-// lane then reads the pairs of ITS vehicle, which other lanes fetched — hence the __syncwarp after the wait.
-template <int BLOCK> struct CkptStreamRec {
-    const double* rec;   // current tile record in HBM
-    size_t rec_stride;
-    long remaining;
-    int slotA, slotB, parity, voff;
-    const double* dbg_base; size_t dbg_total;  // extent of the state-record buffer (AVS_DEBUG)
+// The producer's view of the state-record stream.  The CONSUMER fetches the state tiles (two contiguous cp.async per tile, in the
+// same commit group as the activation tile of the stage that reads it) into a ring of kSRing tiles: record number k, counted
+// from the final state backwards, lives in slot k mod kSRing; reverse stage j reads record j + 1 as its stage input and, at the
+// head of an RK4 step, record j (the step's output) once more.  The producer therefore neither issues nor waits for any copy
+// (round-2 end; before, its own cp.async.wait_group + __syncwarp + prefetch at the head of every stage held 7 % of its stall
+// samples): `advance` is an increment, and the named barrier at the head of the stage (ode_bwd_call2) covers both tiles.
+// kSRing = 8: the slot of record j + 4, which the consumer refills while the producer may still be reading record j, must differ
+// from the slots of records j and j + 1.
+constexpr int kSRing = 8, kSTileCols = 4;  // a tile of kCkTile = 112 doubles takes four columns of kBwdBlock = 32 doubles
+template <int BLOCK> struct CkptStreamRing {
+    int k, slot0, voff;
     __device__ __forceinline__ const double* act() const { return nullptr; }
-    __device__ __forceinline__ RecCol cur() const { return rec_col<BLOCK>(parity ? slotB : slotA, voff); }
-    __device__ __forceinline__ void prefetch_prev() {
-        if (remaining <= 0) return;
-        const double* src = rec - rec_stride;
-        AVS_DBG_RANGE("state tile (reverse prefetch)", src, kCkTile, dbg_base, dbg_total);
-        const int lane = threadIdx.x & 31;
-        double* dst = g_smem + (size_t)(parity ? slotA : slotB) * BLOCK;
-        const unsigned s0 = (unsigned)__cvta_generic_to_shared(dst + lane * 2);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0), "l"(src + lane * 2) : "memory");
-        if (lane < kCkTile / 2 - 32) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + 512u), "l"(src + 64 + lane * 2) : "memory");
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    }
-    __device__ __forceinline__ void init() {
-        AVS_DBG_RANGE("final state tile (reverse init)", rec, kCkTile, dbg_base, dbg_total);
-        const int lane = threadIdx.x & 31;
-        double* dst = g_smem + (size_t)(parity ? slotB : slotA) * BLOCK;
-        for (int c = lane; c < kCkTile; c += 32) dst[c] = __ldg(rec + c);
-        __syncwarp();
-        prefetch_prev();
-    }
-    __device__ __forceinline__ void advance() {
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncwarp();
-        parity ^= 1;
-        rec -= rec_stride;
-        remaining--;
-        prefetch_prev();
-    }
+    __device__ __forceinline__ RecCol cur() const { return rec_col<BLOCK>(slot0 + (k & (kSRing - 1)) * kSTileCols, voff); }
+    __device__ __forceinline__ void advance() { k++; }
 };
 
 // upload the model into this TU's __constant__ copy (stream-ordered, before the launch that reads it).

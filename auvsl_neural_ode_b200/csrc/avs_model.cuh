@@ -1291,9 +1291,6 @@ AVS_HD void ode_bwd_nn_j(const ModelConst& mc, int lane0, const double X[13], do
 // by moving the 2x2 Jacobian's ~216 FP64 instructions per stage into the forward kernel: it got slower by exactly their issue
 // time wherever they were placed), and forming J on top of the layered pass costs ~210 FP64 instructions per wheel and stage
 // more than the layered pass alone, which yields (vx_bar, vy_bar) as a by-product (16 more FMAs).
-#ifndef AVS_BWD_EARLY_GET
-#define AVS_BWD_EARLY_GET 1
-#endif
 template <int WPT, int TERR, class XD, class TIn, class FOut>
 AVS_HD void ode_bwd_nn_p(const ModelConst& mc, int lane0, const double X[13], double ul, double ur, const XD& Xdb, double Xb[13], TIn& tin, FOut& fout) {
     double Sb[6];
@@ -1308,18 +1305,12 @@ AVS_HD void ode_bwd_nn_p(const ModelConst& mc, int lane0, const double X[13], do
         const double qd = (i & 1) ? ur : ul;
         double Fb[3];
         WheelAct act;
-#if AVS_BWD_EARLY_GET
-        double h0[8], h2[8], dzg, dax, day;
-        tin.get(k, h0, h2, dzg, dax, day);  // first: the wait for the tile and the loads overlap the head of the stage
-#endif
         const double cvx = X[10] + (X[8] * kRz - X[9] * ty), cvy = X[11] + (X[9] * tx - X[7] * kRz);
         const double s1 = (qd * kTireRadius - cvx) * (1.0 / kInStd1), s2 = qd * (1.0 / kInStd2), s3 = cvy * (1.0 / kInStd3);
         wheel_aba_act(tx, ty, X, qd, act);
         wheel_aba_bwd(tx, ty, qd, act, Sb, Fb, wb, vb);
-#if !AVS_BWD_EARLY_GET
         double h0[8], h2[8], dzg, dax, day;
         tin.get(k, h0, h2, dzg, dax, day);
-#endif
         const double o0 = Fb[0] * kOutStd0, o1 = Fb[1] * kOutStd1;
         double d2[8], d0[8];
 #pragma unroll
