@@ -60,6 +60,10 @@ def load_counters():
     return c
 
 
+N_SCHEDULERS = 148 * 4  # SM sub-partitions of a B200, one issue slot per cycle each
+SM_CLOCK_MHZ = 1965.0    # maximum SM clock of the pool's B200s (the clocks block of the line reports what the run saw)
+
+
 def roofline_block(counters, kernel, units, kernel_ms, fp64_peak_tflops, hbm_peak_gbs):
     """Roofline of one kernel launch from HARDWARE counters.  The FP64 instruction counts per vehicle-step come from the
     committed ncu capture of this build (profiles/r2_counters.json: smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on,
@@ -95,6 +99,17 @@ def roofline_block(counters, kernel, units, kernel_ms, fp64_peak_tflops, hbm_pea
         "counters": {"file": os.path.relpath(COUNTERS, ROOT), "source_hash": counters.get("source_hash"), "matches_build": counters.get("matches_build"),
                      "captured_ms": k.get("duration_ms"), "registers": k.get("registers"), "grid": k.get("grid"), "block": k.get("block")},
     })
+    # Issue-slot view: on this chip a warp's FP64 instruction occupies its scheduler for two issue cycles, any
+    # other instruction for one, and both rollout kernels are bound by exactly that (measured round 2: 216 extra FP64 instructions
+    # per stage cost the forward kernel their issue time wherever they were placed).  slots = all warp instructions + the FP64 ones
+    # once more; frac_of_chip = slots / (duration x SM clock x 592 schedulers).
+    if k.get("warp_inst_executed") and k.get("warp_inst_pipe_fp64") and k.get("vehicle_steps_per_launch"):
+        per_step = (k["warp_inst_executed"] + k["warp_inst_pipe_fp64"]) / k["vehicle_steps_per_launch"]
+        blk["issue_slots"] = {"warp_inst_per_vehicle_step": k["warp_inst_executed"] / k["vehicle_steps_per_launch"],
+                              "fp64_warp_inst_per_vehicle_step": k["warp_inst_pipe_fp64"] / k["vehicle_steps_per_launch"],
+                              "slots_per_vehicle_step": per_step,
+                              "frac_of_chip": per_step * units / (sec * SM_CLOCK_MHZ * 1e6 * N_SCHEDULERS),
+                              "definition": "(warp instructions + FP64 warp instructions) / (duration x 1965 MHz x 592 schedulers)"}
     return blk
 
 
