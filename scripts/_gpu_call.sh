@@ -1,4 +1,5 @@
-python scripts/ncu_targets.py once > gpurun_out/ncu_targets_plain.log 2>&1; echo "targets rc=$?"
-ncu --set full --metrics smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,sm__inst_executed_pipe_fp64.sum --clock-control none --import-source on -k regex:rollout -c 4 -f -o gpurun_out/prof_r2h python scripts/ncu_targets.py once > gpurun_out/ncu_r2h.log 2>&1; echo "ncu rc=$?"; tail -2 gpurun_out/ncu_r2h.log
-python bench.py --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1; echo "bench plain rc=$?"
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r2h.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch_r2h.log 2>&1; echo "launch list rc=$?"
+python bench.py > gpurun_out/bench_r2h.json 2> gpurun_out/bench_r2h.err; echo "bench rc=$?"
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_r2h_ref.json 2> gpurun_out/bench_r2h_ref.err; echo "ref rc=$?"; tail -c 600 gpurun_out/bench_r2h_ref.json
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python scripts/quick_gpu.py 8192 600 200 2 2>&1 | grep "grad=" 
+python scripts/quick_gpu.py 16384 600 200 2 2>&1 | grep "grad="
