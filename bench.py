@@ -494,7 +494,7 @@ def run_b200(args):
             "config": {"workload": f"configs[2] per GPU: {N} rollouts x {T} rows, NN tire model (load_model weights), flat terrain, forward + adjoint "
                                    "w.r.t. tire-NN weights + explosion filter + (all-reduce) + RMSProp",
                        "trajectories_per_gpu": N, "rows": T, "substeps": sub, "vehicle_steps_per_step": world * steps_per_call,
-                       "l2": "no explicit flush: every step streams 24.5 GB of state + activation records (>> 126 MB L2) out to HBM in the "
+                       "l2": "no explicit flush: every step streams 22.4 GB of state + activation records (>> 126 MB L2) out to HBM in the "
                              "forward sweep and back in the reverse sweep",
                        "parallelism": f"dp{world} (shard by trajectory, one ncclAllReduce of 418 fp64 per step behind the C ABI: avs_allreduce_dev)"},
             "clocks": clocks, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
