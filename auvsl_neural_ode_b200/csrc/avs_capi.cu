@@ -48,7 +48,7 @@ struct avs_ctx {
     double* d_params = nullptr;  // [416] device copy (RMSProp operates here)
     double* d_sq = nullptr;      // [416] RMSProp state
     bool params_dirty_on_device = false;
-    DevBuf grid_h, grid_s, ztab, exptab;
+    DevBuf grid_h, grid_s, ztab;
     DevBuf ckpt, act, gps, loss, reduced, flags, settle;
     DevBuf in_x0, in_ctrl, in_gt, out_list, out_final, io_a, io_b, io_c;
     DevBuf margins;
@@ -248,12 +248,6 @@ int avs_create(avs_ctx** out, int device, int tire_model) {
              cudaMemcpy(ctx->ztab.p, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess;
         ctx->mc.ztab = ctx->ztab.as<double>();
     }
-    if (ok) {  // exponential table of the 8-wide tanh
-        double tab[32];
-        build_exptab(tab);
-        ok = ctx->exptab.reserve(sizeof(tab)) == cudaSuccess && cudaMemcpy(ctx->exptab.p, tab, sizeof(tab), cudaMemcpyHostToDevice) == cudaSuccess;
-        ctx->mc.exptab = ctx->exptab.as<double>();
-    }
     if (!ok) { avs_destroy(ctx); return AVS_E_CUDA; }
     if (cudaMemcpy(ctx->d_params, ctx->params, sizeof(ctx->params), cudaMemcpyHostToDevice) != cudaSuccess) { avs_destroy(ctx); return AVS_E_CUDA; }
     *out = ctx;
@@ -266,7 +260,7 @@ void avs_destroy(avs_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->comm && nccl_api()->CommDestroy) nccl_api()->CommDestroy(ctx->comm);
     ctx->margins.release();
-    DevBuf* bufs[] = {&ctx->grid_h, &ctx->grid_s, &ctx->ztab, &ctx->exptab, &ctx->ckpt, &ctx->act, &ctx->gps, &ctx->loss, &ctx->reduced, &ctx->flags, &ctx->settle,
+    DevBuf* bufs[] = {&ctx->grid_h, &ctx->grid_s, &ctx->ztab, &ctx->ckpt, &ctx->act, &ctx->gps, &ctx->loss, &ctx->reduced, &ctx->flags, &ctx->settle,
                       &ctx->in_x0, &ctx->in_ctrl, &ctx->in_gt, &ctx->out_list, &ctx->out_final, &ctx->io_a, &ctx->io_b, &ctx->io_c};
     for (DevBuf* b : bufs) b->release();
     if (ctx->d_params) cudaFree(ctx->d_params);

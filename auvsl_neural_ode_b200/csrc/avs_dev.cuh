@@ -90,30 +90,13 @@ template <int TIRE, int TERR, int BLOCK, bool STORE_ACT, bool MARGIN = false> st
 // rolled loop in the kernel contains nothing but four calls.  Scratch slots: X 0 | ACC 13 | T 26 | INV 56.
 // tid = threadIdx.x, handed in by the caller: the non-inlined callee would otherwise re-read the special register (S2R, a
 // short-scoreboard wait at the head of every call: forward+store 11.25 -> 11.06 ms, round 2)
-#ifndef AVS_CK4
-#define AVS_CK4 0
-#endif
 template <int TERR, int BLOCK, bool STORE>
 __device__ __noinline__ void ode_fwd_stage_call(int tid, int lane0, double ul, double ur, int s, double* rec, double* act) {
     const Scratch<BLOCK> X{g_smem + tid}, ACC{g_smem + 13 * BLOCK + tid}, T{g_smem + 26 * BLOCK + tid}, INV{g_smem + 56 * BLOCK + tid};
     double x[13], k[13];
 #pragma unroll
     for (int c = 0; c < 13; c++) x[c] = T[c];
-#if AVS_CK4
-    // State record: the four lanes of a vehicle share the store.  Lane k writes pairs k and k + 4 (lane 3: pair 3 twice) of its
-    // vehicle straight from the scratch columns (a lane-dependent column index is free in shared memory, in registers it
-    // would be a chain of selects): two unconditional STG.128 per lane, no divergent writer region, no write-after-read wait
-    // on the x registers.  Tail lanes mirror the last vehicle and rewrite its bytes with the same values.
-    if (STORE) {
-        const int c0 = 26 + 2 * lane0, r2 = lane0 < 3 ? lane0 + 4 : 3, c2 = 26 + 2 * r2, c3 = (lane0 == 2) ? 56 : c2 + 1;
-        const double a0 = g_smem[c0 * BLOCK + tid], a1 = g_smem[(c0 + 1) * BLOCK + tid];
-        const double b0 = g_smem[c2 * BLOCK + tid], b1 = g_smem[c3 * BLOCK + tid];
-        *reinterpret_cast<double2*>(rec + (size_t)lane0 * kCkPairStride) = make_double2(a0, a1);
-        *reinterpret_cast<double2*>(rec + (size_t)r2 * kCkPairStride) = make_double2(b0, b1);
-    }
-#else
     if (STORE && rec) CkptSink::ckpt_store(rec, x, INV[0]);
-#endif
     ode_fwd<1, TIRE_NN, TERR, STORE>(c_mc, lane0, x, ul, ur, k, nullptr, ActOutPtr{act, kActPairStride});
     const double h = kDt;
     double inv;
@@ -145,11 +128,7 @@ template <int TERR, int BLOCK, bool STORE> struct FusedStep {
     __device__ __forceinline__ void operator()(size_t step, double& inv_carry) const {
         const size_t NK = (size_t)a.Nc;
         const size_t rec_stride = ck_rec_stride(NK);
-#if AVS_CK4
-        double* rec = STORE ? a.ckpt + (step * 4) * rec_stride + ck_lane_offset(n) : nullptr;  // every lane stores (see the callee)
-#else
         double* rec = (STORE && writer) ? a.ckpt + (step * 4) * rec_stride + ck_lane_offset(n) : nullptr;
-#endif
         // activation records: warp-tiled (avs_model.cuh, ActOutPtr); addressed by the thread's own global lane index, so
         // tail lanes (which mirror the last vehicle) write into the padding of the last tile
         const size_t act_stride = act_stage_doubles(NK);

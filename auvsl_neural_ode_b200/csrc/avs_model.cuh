@@ -85,7 +85,6 @@ struct ModelConst {
     double AIinv[6][6];                   // (I_b + sum X^T Ia X)^-1
     double bek[5];                        // Bekker soil 5-vector as passed to setParams (BekkerDynamics.cpp:12-21)
     GridTerrain grid;
-    const double* exptab;                 // [32] 2^(1 + j/32), j = 0..31 (build_exptab): table of the 8-wide tanh, or nullptr
     const double* ztab;                   // [kZTabRows][kZTabRow] piecewise polynomials of the fixed z-net and its derivative (build_ztab)
     int terr_kind;                        // used by the TERR_DYN instantiations
     // optional 10-angle contact search (HybridDynamics::get_tire_cpts_sinkages_fancy, HybridDynamics.cpp:258-316), TERR_DYN
@@ -234,86 +233,6 @@ template <int W> AVS_HD void tanh_vec(double* x) {
 #pragma unroll
     for (int i = 0; i < W; i++) x[i] = copysign(t[i], x[i]);
 }
-
-// ---- 8-wide tanh with a 32-entry exponential table (the hot path of the forward sweep) -----------------------------------------
-// tanh|x| = 1 - 2e/(1 + e), e = exp(-2|x|) = 2^k 2^(j/32) exp(r), 32 k + j = round(-2|x| 32/ln2), |r| <= ln2/64, so exp(r) needs
-// degree 6 instead of 11 (truncation 3.5e-18).  Everything is written in r' = -r/2 = |x| + m ln2/64 so that -2|x| is never formed,
-// and the table holds 2 * 2^(j/32) so that 2e falls out of the exponent patch: 16 FP64-pipe instructions + 1 MUFU + one 8-byte
-// table load per element (the table is 256 bytes: two L1 lines) instead of 22.  The 16 tanh per wheel and ODE evaluation are
-// 47 % of the forward kernel's FP64 instructions, and that part of the stage is pipe-bound.
-// Absolute error <= ~3e-16 like tanh_vec (table entries are rounded: 1.1e-16 relative in e).
-template <int W> AVS_HD void tanh_tab_vec(const double* __restrict__ tab, double* x) {
-    const double MAGIC = 6755399441055744.0;
-    const double C = -92.332482616893656768;                                // -64 / ln 2
-    const double L_HI = 6.93147180559945286e-01 / 64.0, L_LO = 2.31904681384629956e-17 / 64.0;  // ln2 / 64, hi + lo
-    double ax[W], t[W], r[W], p[W], e2[W];
-#pragma unroll
-    for (int i = 0; i < W; i++) { const double a = fabs(x[i]); ax[i] = a < 20.0 ? a : 20.0; }   // tanh(20) = 1 - 8e-18
-#pragma unroll
-    for (int i = 0; i < W; i++) t[i] = fma(ax[i], C, MAGIC);                // m = round(-64 |x| / ln2) in the low mantissa bits
-#pragma unroll
-    for (int i = 0; i < W; i++) r[i] = t[i] - MAGIC;
-#pragma unroll
-    for (int i = 0; i < W; i++) ax[i] = fma(r[i], L_HI, ax[i]);
-#pragma unroll
-    for (int i = 0; i < W; i++) r[i] = fma(r[i], L_LO, ax[i]);              // r' = |x| + m ln2/64 in [-ln2/128, ln2/128]; exp(-2 r') follows
-#pragma unroll
-    for (int i = 0; i < W; i++) {
-#if defined(__CUDA_ARCH__)
-        const int m = __double2loint(t[i]);
-        e2[i] = __ldg(tab + (m & 31));
-        e2[i] = __hiloint2double(__double2hiint(e2[i]) + ((m >> 5) << 20), __double2loint(e2[i]));
-#else
-        const int64_t m = (int64_t)(t[i] - MAGIC);
-        e2[i] = ldexp(tab[m & 31], (int)(m >> 5));
-#endif
-    }
-    // exp(-2 r') = 1 + r' q(r'),  q = -2 + 2 r' - 4/3 r'^2 + 2/3 r'^3 - 4/15 r'^4 + 4/45 r'^5
-#pragma unroll
-    for (int i = 0; i < W; i++) p[i] = fma(8.8888888888888892e-02, r[i], -2.6666666666666666e-01);
-#pragma unroll
-    for (int i = 0; i < W; i++) p[i] = fma(p[i], r[i], 6.6666666666666663e-01);
-#pragma unroll
-    for (int i = 0; i < W; i++) p[i] = fma(p[i], r[i], -1.3333333333333333e+00);
-#pragma unroll
-    for (int i = 0; i < W; i++) p[i] = fma(p[i], r[i], 2.0);
-#pragma unroll
-    for (int i = 0; i < W; i++) p[i] = fma(p[i], r[i], -2.0);
-#pragma unroll
-    for (int i = 0; i < W; i++) p[i] = fma(p[i], r[i], 1.0);
-#pragma unroll
-    for (int i = 0; i < W; i++) e2[i] *= p[i];                              // 2 e
-#pragma unroll
-    for (int i = 0; i < W; i++) ax[i] = fma(e2[i], 0.5, 1.0);               // d = 1 + e in [1, 2]
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-    for (int i = 0; i < W; i++) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r[i]) : "d"(ax[i]));
-#pragma unroll
-    for (int i = 0; i < W; i++) t[i] = fma(-ax[i], r[i], 1.0);
-#pragma unroll
-    for (int i = 0; i < W; i++) t[i] = fma(t[i], t[i], t[i]);
-#pragma unroll
-    for (int i = 0; i < W; i++) r[i] = fma(r[i], t[i], r[i]);
-#else
-#pragma unroll
-    for (int i = 0; i < W; i++) r[i] = 1.0 / ax[i];
-#endif
-#pragma unroll
-    for (int i = 0; i < W; i++) t[i] = fma(-e2[i], r[i], 1.0);
-#pragma unroll
-    for (int i = 0; i < W; i++) x[i] = copysign(t[i], x[i]);
-}
-inline void build_exptab(double* tab32) {
-    for (int j = 0; j < 32; j++) tab32[j] = (double)(2.0L * exp2l((long double)j / 32.0L));
-}
-#ifndef AVS_TANH_TAB
-#define AVS_TANH_TAB 0
-#endif
-#if AVS_TANH_TAB
-#define AVS_TANH8(mc, v) tanh_tab_vec<8>((mc).exptab, v)
-#else
-#define AVS_TANH8(mc, v) tanh_vec<8>(v)
-#endif
 
 AVS_HD double rsqrt_f64(double x) {  // for quaternion re-normalisation, x ~ 1
 #if defined(__CUDA_ARCH__)
@@ -565,7 +484,7 @@ AVS_HD void tire_nn_fwd(const ModelConst& mc, double vx, double vy, double w, do
     for (int j = 0; j < 8; j++) a.h0[j] = fma(mc.W0[j][1], a.s2, a.h0[j]);
 #pragma unroll
     for (int j = 0; j < 8; j++) a.h0[j] = fma(mc.W0[j][2], a.s3, a.h0[j]);
-    AVS_TANH8(mc, a.h0);
+    tanh_vec<8>(a.h0);
 #pragma unroll
     for (int j = 0; j < 8; j++) a.h2[j] = mc.W2[j][0] * a.h0[0];
 #pragma unroll
@@ -573,7 +492,7 @@ AVS_HD void tire_nn_fwd(const ModelConst& mc, double vx, double vy, double w, do
 #pragma unroll
         for (int j = 0; j < 8; j++) a.h2[j] = fma(mc.W2[j][k], a.h0[k], a.h2[j]);
     }
-    AVS_TANH8(mc, a.h2);
+    tanh_vec<8>(a.h2);
     // two output rows, each as two interleaved partial sums
     double f0a = mc.W4[0][0] * a.h2[0], f0b = mc.W4[0][1] * a.h2[1];
     double f1a = mc.W4[1][0] * a.h2[0], f1b = mc.W4[1][1] * a.h2[1];
@@ -646,65 +565,6 @@ AVS_HD void tire_nn_bwd(const ModelConst& mc, const NNAct& a, const double Fbar[
     vxb = -(s1a + s1b) * (1.0 / kInStd1);
     vyb = (s3a + s3b) * (1.0 / kInStd3);
     zrb = (oz * a.dz4) * (1.0 / kInStd0);
-}
-
-// ---- the tire-network adjoint split in two (reverse kernel: producer warp / consumer warp) ----------------------------
-// The state adjoint needs only  (vx_bar, vy_bar) = J^T (Fx_bar, Fy_bar)  with the 2x2 input-output Jacobian of the xy-net,
-//   J[r][c] = sum_k W0[k][c] d0[k] (sum_j W2[j][k] d2[j] W4[r][j]),   d = 1 - h^2,
-// which depends on the stored activations and the weights only — it can be formed BEFORE the adjoint of the stage runs.
-// The layered back-propagation (delta2, delta0) is needed for the weight gradient alone.  Scalings folded in:
-//   vx_bar = Fx_bar jxx + Fy_bar jyx ,  vy_bar = Fx_bar jxy + Fy_bar jyy.
-struct TireJac { double jxx, jyx, jxy, jyy; };
-AVS_HD void tire_jacobian(const ModelConst& mc, const double h0[8], const double h2[8], TireJac& J) {
-    double d0[8], d2[8], u0[8], u1[8], v0[8], v1[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) { d2[k] = fma(-h2[k], h2[k], 1.0); d0[k] = fma(-h0[k], h0[k], 1.0); }
-#pragma unroll
-    for (int j = 0; j < 8; j++) { u0[j] = d2[j] * mc.W4[0][j]; u1[j] = d2[j] * mc.W4[1][j]; }
-#pragma unroll
-    for (int k = 0; k < 8; k++) { v0[k] = mc.W2[0][k] * u0[0]; v1[k] = mc.W2[0][k] * u1[0]; }
-#pragma unroll
-    for (int j = 1; j < 8; j++) {
-#pragma unroll
-        for (int k = 0; k < 8; k++) { v0[k] = fma(mc.W2[j][k], u0[j], v0[k]); v1[k] = fma(mc.W2[j][k], u1[j], v1[k]); }
-    }
-#pragma unroll
-    for (int k = 0; k < 8; k++) { v0[k] *= d0[k]; v1[k] *= d0[k]; }
-    double a00 = mc.W0[0][0] * v0[0], a02 = mc.W0[0][2] * v0[0], a10 = mc.W0[0][0] * v1[0], a12 = mc.W0[0][2] * v1[0];
-    double b00 = mc.W0[1][0] * v0[1], b02 = mc.W0[1][2] * v0[1], b10 = mc.W0[1][0] * v1[1], b12 = mc.W0[1][2] * v1[1];
-#pragma unroll
-    for (int k = 2; k < 8; k += 2) {
-        a00 = fma(mc.W0[k][0], v0[k], a00); a02 = fma(mc.W0[k][2], v0[k], a02); a10 = fma(mc.W0[k][0], v1[k], a10); a12 = fma(mc.W0[k][2], v1[k], a12);
-        b00 = fma(mc.W0[k + 1][0], v0[k + 1], b00); b02 = fma(mc.W0[k + 1][2], v0[k + 1], b02);
-        b10 = fma(mc.W0[k + 1][0], v1[k + 1], b10); b12 = fma(mc.W0[k + 1][2], v1[k + 1], b12);
-    }
-    // s1 = (w R - vx) / std1 (minus sign), s3 = vy / std3 ; o_r = F_bar_r * out_std_r
-    J.jxx = -(a00 + b00) * (kOutStd0 / kInStd1); J.jyx = -(a10 + b10) * (kOutStd1 / kInStd1);
-    J.jxy = (a02 + b02) * (kOutStd0 / kInStd3);  J.jyy = (a12 + b12) * (kOutStd1 / kInStd3);
-}
-// operands of the three weight-gradient outer products (order of grad_outer) from the stored activations, the two
-// output adjoints (Fx_bar, Fy_bar) and the scaled inputs — the first half of tire_nn_bwd
-AVS_HD void tire_wgrad_ops(const ModelConst& mc, const double h0[8], const double h2[8], double fxb, double fyb, double s1, double s2, double s3,
-                           double op[kGradOps]) {
-    const double o0 = fxb * kOutStd0, o1 = fyb * kOutStd1;
-    double* d2 = op + 10; double* d0 = op + 26;
-    op[0] = o0; op[1] = o1;
-#pragma unroll
-    for (int k = 0; k < 8; k++) { op[2 + k] = h2[k]; op[18 + k] = h0[k]; }
-    op[34] = s1; op[35] = s2; op[36] = s3;
-#pragma unroll
-    for (int k = 0; k < 8; k++) d2[k] = fma(mc.W4[1][k], o1, mc.W4[0][k] * o0);
-#pragma unroll
-    for (int k = 0; k < 8; k++) d2[k] *= fma(-h2[k], h2[k], 1.0);
-#pragma unroll
-    for (int k = 0; k < 8; k++) d0[k] = mc.W2[0][k] * d2[0];
-#pragma unroll
-    for (int j = 1; j < 8; j++) {
-#pragma unroll
-        for (int k = 0; k < 8; k++) d0[k] = fma(mc.W2[j][k], d2[j], d0[k]);
-    }
-#pragma unroll
-    for (int k = 0; k < 8; k++) d0[k] *= fma(-h0[k], h0[k], 1.0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1174,73 +1034,13 @@ AVS_HD void ode_bwd_nn(const ModelConst& mc, int lane0, const double X[13], doub
     quat_to_R_bwd(X, Rb, Xb);
 }
 
-// The same adjoint with the tire network split off (reverse kernel): `jin.get(k, J, dzg, dax, day)` delivers, for this
-// thread's k-th wheel, the xy-net Jacobian, the gated z-branch derivative and the terrain gradient (all functions of the
-// stage's stored activations only); `fout.put(k, Fx_bar, Fy_bar, s1, s2, s3)` hands over what the weight gradient needs.
-template <int WPT, int TERR, class XD, class JIn, class FOut>
-AVS_HD void ode_bwd_nn_j(const ModelConst& mc, int lane0, const double X[13], double ul, double ur, const XD& Xdb, double Xb[13], JIn& jin, FOut& fout) {
-    double Sb[6];
-    base_bwd_S(mc, Xdb, Sb);
-    double gx[3] = {0, 0, 0}, gy[3] = {0, 0, 0}, gs[3] = {0, 0, 0};  // sum sx*cpb, sum sy*cpb, sum cpb
-    double wb[3] = {0, 0, 0}, vb[3] = {0, 0, 0};
-#pragma unroll
-    for (int k = 0; k < WPT; k++) {
-        const int i = lane0 + k;
-        double tx, ty;
-        wheel_sign(i, tx, ty);
-        const double qd = (i & 1) ? ur : ul;
-        double Fb[3];
-        WheelAct act;
-        const double cvx = X[10] + (X[8] * kRz - X[9] * ty), cvy = X[11] + (X[9] * tx - X[7] * kRz);
-        const double s1 = (qd * kTireRadius - cvx) * (1.0 / kInStd1), s2 = qd * (1.0 / kInStd2), s3 = cvy * (1.0 / kInStd3);
-        wheel_aba_act(tx, ty, X, qd, act);
-        wheel_aba_bwd(tx, ty, qd, act, Sb, Fb, wb, vb);
-        TireJac J;
-        double dzg, dax, day;
-        jin.get(k, J, dzg, dax, day);
-        fout.put(k, Fb[0], Fb[1], s1, s2, s3);
-        double cvb[3];
-        cvb[0] = fma(Fb[1], J.jyx, Fb[0] * J.jxx);
-        cvb[1] = fma(Fb[1], J.jyy, Fb[0] * J.jxy);
-        cvb[2] = kNNDamp * Fb[2];
-        const double sinkb = (Fb[2] * kOutStd2 * dzg) * (1.0 / kInStd0);
-        // cv = v + w x r
-        vb[0] += cvb[0]; vb[1] += cvb[1]; vb[2] += cvb[2];
-        wb[0] += ty * cvb[2] - kRz * cvb[1];
-        wb[1] += kRz * cvb[0] - tx * cvb[2];
-        wb[2] += tx * cvb[1] - ty * cvb[0];
-        // sink = alt(cpx, cpy) - cpz
-        const double cpb0 = (TERR == TERR_FLAT) ? 0.0 : sinkb * dax, cpb1 = (TERR == TERR_FLAT) ? 0.0 : sinkb * day, cpb2 = -sinkb;
-        const double sx = (i & 2) ? -1.0 : 1.0, sy = (i & 1) ? -1.0 : 1.0;
-        gx[0] += sx * cpb0; gx[1] += sx * cpb1; gx[2] += sx * cpb2;
-        gy[0] += sy * cpb0; gy[1] += sy * cpb1; gy[2] += sy * cpb2;
-        gs[0] += cpb0; gs[1] += cpb1; gs[2] += cpb2;
-    }
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-        if (!(TERR == TERR_FLAT && c < 2)) { gx[c] = Group<WPT>::sum(gx[c]); gy[c] = Group<WPT>::sum(gy[c]); gs[c] = Group<WPT>::sum(gs[c]); }
-        wb[c] = Group<WPT>::sum(wb[c]); vb[c] = Group<WPT>::sum(vb[c]);
-    }
-    double R[9], Rb[9];
-    quat_to_R(X, R);
-    base_bwd_rest(R, X, Xdb, Sb, Xb, Rb);
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-        Rb[3 * c + 0] = fma(kTx, gx[c], Rb[3 * c + 0]);
-        Rb[3 * c + 1] = fma(kTy, gy[c], Rb[3 * c + 1]);
-        Rb[3 * c + 2] = fma(kRz, gs[c], Rb[3 * c + 2]);
-        Xb[4 + c] += gs[c];
-        Xb[7 + c] += wb[c];
-        Xb[10 + c] += vb[c];
-    }
-    quat_to_R_bwd(X, Rb, Xb);
-}
 // The same adjoint with the LAYERED back-propagation of the tire network run right here, on the state chain (reverse kernel,
 // end of round 2): `tin.get(k, h0, h2, dzg, dax, day)` delivers the stored activations of this thread's k-th wheel,
 // `fout.put(k, o0, o1, s1, s2, s3, d2, d0)` hands over the operands of the three weight-gradient outer products
 //   dW4 += (o0, o1) (x) h2 ,  dW2 += d2 (x) h0 ,  dW0 += d0 (x) (s1, s2, s3).
-// Arithmetic and order are those of tire_nn_bwd, so the result is bit-identical to ode_bwd_nn.  Why not the Jacobian split
-// above: both rollout kernels turned out to be bound by issue slots (an FP64 instruction takes two, any other one; measured
+// Arithmetic and order are those of tire_nn_bwd, so the result is bit-identical to ode_bwd_nn.  Why not a separately formed
+// 2x2 Jacobian of the xy-net for the state chain (the design until late in round 2): both rollout
+// kernels turned out to be bound by issue slots (an FP64 instruction takes two, any other one; measured
 // by moving the 2x2 Jacobian's ~216 FP64 instructions per stage into the forward kernel: it got slower by exactly their issue
 // time wherever they were placed), and forming J on top of the layered pass costs ~210 FP64 instructions per wheel and stage
 // more than the layered pass alone, which yields (vx_bar, vy_bar) as a by-product (16 more FMAs).
@@ -1342,25 +1142,6 @@ template <class Acc> struct LayeredFromRecords {
         acc.record(op);
     }
 };
-// host-side (and reference) providers: Jacobian formed on the spot from the activation records, weight gradient applied at once
-template <class Acc> struct JFromRecords {
-    const ModelConst& mc; const double* act; Acc& acc;  // act = four consecutive kActLen-double records
-    double h0[8], h2[8];
-    AVS_HD void get(int k, TireJac& J, double& dzg, double& dax, double& day) {
-        NNAct a;
-        act_load(a, dax, day, ActInPtr{act + (size_t)k * kActLen});
-        dzg = a.dz4;
-#pragma unroll
-        for (int i = 0; i < 8; i++) { h0[i] = a.h0[i]; h2[i] = a.h2[i]; }
-        tire_jacobian(mc, h0, h2, J);
-    }
-    AVS_HD void put(int, double fxb, double fyb, double s1, double s2, double s3) {
-        double op[kGradOps];
-        tire_wgrad_ops(mc, h0, h2, fxb, fyb, s1, s2, s3, op);
-        acc.record(op);
-    }
-};
-
 // ------------------------------------------------------------------------------------------------
 // RK4 step with per-stage quaternion re-normalisation (HybridDynamics::RK4, HybridDynamics.cpp:461-502)
 // ------------------------------------------------------------------------------------------------
@@ -1477,7 +1258,8 @@ template <int WPT, int TERR, class Acc> struct OdeBwdInline {
         double X[13], Xb[13];
 #pragma unroll
         for (int c = 0; c < 13; c++) X[c] = XS[c];
-        ode_bwd_nn<WPT, TERR>(mc, lane0, X, ul, ur, KB, Xb, acc, ActInPtr{act});
+        LayeredFromRecords<Acc> io{act, acc};  // the adjoint the reverse kernel's producer warp runs (bit-identical to ode_bwd_nn)
+        ode_bwd_nn_p<WPT, TERR>(mc, lane0, X, ul, ur, KB, Xb, io, io);
         rk4_bwd_stage_update(XS, Xb, s, LAM, YB, KB);
     }
 };

@@ -40,9 +40,6 @@ static void fill_mc(ModelConst& mc, const double* p416, const double* zw152, con
     mc.terr_kind = 0;
     static std::vector<double> ztab;
     if (zw152) { ztab.resize((size_t)kZTabRows * kZTabRow); build_ztab(mc.Z0, mc.Z2, mc.Z4, ztab.data()); mc.ztab = ztab.data(); }
-    static double etab[32];
-    build_exptab(etab);
-    mc.exptab = etab;
     mc.grid.height = height; mc.grid.soil = soil; mc.grid.nx = nx; mc.grid.ny = ny;
     mc.grid.x0 = x0; mc.grid.y0 = y0; mc.grid.inv_dx = 1.0 / dx; mc.grid.inv_dy = 1.0 / dy;
 }
@@ -152,10 +149,10 @@ void hc_zweights(double* out152) { memcpy(out152, kFixedZ0, 64); memcpy(out152 +
 void hc_default_params(double* p416) { for (int k = 0; k < 4; k++) { memcpy(p416 + 104 * k, kDefaultW0, 192); memcpy(p416 + 104 * k + 24, kDefaultW2, 512); memcpy(p416 + 104 * k + 88, kDefaultW4, 128); } }
 void hc_aiinv(double* out36) { double A[6][6]; compute_AIinv(A); memcpy(out36, A, sizeof(A)); }
 double hc_tanh(double x) { return tanh_f64(x); }
-double hc_tanh_tab(double x) {
-    double tab[32], v[1] = {x};
-    build_exptab(tab);
-    tanh_tab_vec<1>(tab, v);
+// the tanh of the kernels' hot path (tanh_vec: 19 FP64 instructions per element on the device; the CPU build divides exactly)
+double hc_tanh_vec(double x) {
+    double v[1] = {x};
+    tanh_vec<1>(v);
     return v[0];
 }
 double hc_ztab(double s0, double* dz) {
@@ -198,22 +195,6 @@ void hc_ode_vjp(const hc_model* m, const double* X13, const double* u2, const do
         case 1: ode_fwd<4, 0, 1, true>(mc, 0, X13, u2[0], u2[1], Xd, nullptr, ActOutPtr{actrec}); ode_bwd_nn<4, 1>(mc, 0, X13, u2[0], u2[1], KB, Xb13, acc, ActInPtr{actrec}); break;
         case 2: ode_fwd<4, 0, 2, true>(mc, 0, X13, u2[0], u2[1], Xd, nullptr, ActOutPtr{actrec}); ode_bwd_nn<4, 2>(mc, 0, X13, u2[0], u2[1], KB, Xb13, acc, ActInPtr{actrec}); break;
         default: ode_fwd<4, 0, 3, true>(mc, 0, X13, u2[0], u2[1], Xd, nullptr, ActOutPtr{actrec}); ode_bwd_nn<4, 3>(mc, 0, X13, u2[0], u2[1], KB, Xb13, acc, ActInPtr{actrec}); break;
-    }
-    memcpy(gW104, acc.g, sizeof(acc.g));
-}
-// the same product through the split tire adjoint (Jacobian + separate weight-gradient operands) the reverse kernel uses
-void hc_ode_vjp_split(const hc_model* m, const double* X13, const double* u2, const double* Xdb13, double* Xb13, double* gW104) {
-    ModelConst mc; mk(m, mc);
-    HostAcc acc;
-    double kb[13], Xd[13], actrec[kActLen * 4];
-    memcpy(kb, Xdb13, sizeof(kb));
-    Scratch<1> KB{kb};
-    JFromRecords<HostAcc> io{mc, actrec, acc};
-    switch (m->terr) {
-        case 0: ode_fwd<4, 0, 0, true>(mc, 0, X13, u2[0], u2[1], Xd, nullptr, ActOutPtr{actrec}); ode_bwd_nn_j<4, 0>(mc, 0, X13, u2[0], u2[1], KB, Xb13, io, io); break;
-        case 1: ode_fwd<4, 0, 1, true>(mc, 0, X13, u2[0], u2[1], Xd, nullptr, ActOutPtr{actrec}); ode_bwd_nn_j<4, 1>(mc, 0, X13, u2[0], u2[1], KB, Xb13, io, io); break;
-        case 2: ode_fwd<4, 0, 2, true>(mc, 0, X13, u2[0], u2[1], Xd, nullptr, ActOutPtr{actrec}); ode_bwd_nn_j<4, 2>(mc, 0, X13, u2[0], u2[1], KB, Xb13, io, io); break;
-        default: ode_fwd<4, 0, 3, true>(mc, 0, X13, u2[0], u2[1], Xd, nullptr, ActOutPtr{actrec}); ode_bwd_nn_j<4, 3>(mc, 0, X13, u2[0], u2[1], KB, Xb13, io, io); break;
     }
     memcpy(gW104, acc.g, sizeof(acc.g));
 }

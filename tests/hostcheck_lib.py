@@ -25,8 +25,8 @@ def lib():
         _lib = C.CDLL(_SO)
         _lib.hc_tanh.restype = C.c_double
         _lib.hc_tanh.argtypes = [C.c_double]
-        _lib.hc_tanh_tab.restype = C.c_double
-        _lib.hc_tanh_tab.argtypes = [C.c_double]
+        _lib.hc_tanh_vec.restype = C.c_double
+        _lib.hc_tanh_vec.argtypes = [C.c_double]
         _lib.hc_ztab.restype = C.c_double
         _lib.hc_ztab.argtypes = [C.c_double, C.c_void_p]
     return _lib
@@ -120,13 +120,6 @@ def ode_vjp_layered(m, X13, u, Xdb):
     X13, u, Xdb = _f64(X13), _f64(u), _f64(Xdb)
     xb, g = np.zeros(13), np.zeros(104)
     lib().hc_ode_vjp_layered(C.byref(m), _p(X13), _p(u), _p(Xdb), _p(xb), _p(g))
-    return xb, g
-
-
-def ode_vjp_split(m, X13, u, Xdb):
-    X13, u, Xdb = _f64(X13), _f64(u), _f64(Xdb)
-    xb, g = np.zeros(13), np.zeros(104)
-    lib().hc_ode_vjp_split(C.byref(m), _p(X13), _p(u), _p(Xdb), _p(xb), _p(g))
     return xb, g
 
 

@@ -26,6 +26,10 @@ def test_tanh_accuracy():
     xs = np.concatenate([rng.normal(0, 3, 4000), rng.normal(0, 0.01, 1000), [0.0, 1e-300, 19.9, 30.0, -40.0, 400.0, -1e4]])
     err = max(abs(hc.lib().hc_tanh(float(x)) - np.tanh(x)) for x in xs)
     assert err <= 4.5e-16
+    # the 8-wide tanh of the kernels' hot path (tanh_vec: -2|x| folded into the polynomial, one-word reduction, 1 - 2e/(1+e))
+    err_vec = max(abs(hc.lib().hc_tanh_vec(float(x)) - np.tanh(x)) for x in xs)
+    print(f"tanh_vec: max abs error {err_vec:.2e}")
+    assert err_vec <= 4.5e-16
 
 
 def test_ztable_matches_fixed_z_network():
@@ -226,10 +230,10 @@ def test_bekker_vectorised_quadrature_vs_oracle_random_inputs():
     assert worst < 1e-10
 
 
-def test_split_tire_adjoint_matches_layered_adjoint():
-    """The reverse kernel cuts the tire-network adjoint in two: the state chain uses the 2x2 input-output Jacobian
-    (tire_jacobian), the weight gradient the layered back-propagation (tire_wgrad_ops).  Against the one-piece adjoint
-    (ode_bwd_nn / tire_nn_bwd) on all terrains: state adjoint equal to rounding, weight gradient bit-identical."""
+def test_producer_adjoint_is_the_one_piece_adjoint():
+    """The reverse kernel's producer warp runs ode_bwd_nn_p: the layered back-propagation of the tire network on the state chain,
+    the operands of the three weight-gradient outer products handed to the consumer warp.  Against the one-piece adjoint
+    (ode_bwd_nn / tire_nn_bwd, applied at once) on all terrains: state adjoint and weight gradient bit-identical."""
     rng = np.random.default_rng(11)
     G = _golden()
     for terr in (po.FLAT, po.SLOPE, po.BUMPY):
@@ -238,11 +242,6 @@ def test_split_tire_adjoint_matches_layered_adjoint():
             X, u = G[f"ode_nn_X_{terr}"][i][LIVE], G[f"ode_nn_U_{terr}"][i]
             lam = rng.normal(size=13)
             xb, gW = hc.ode_vjp(m, X, u, lam)
-            xb2, gW2 = hc.ode_vjp_split(m, X, u, lam)
-            np.testing.assert_allclose(xb2, xb, rtol=0, atol=1e-14 * np.abs(xb).max())
-            np.testing.assert_array_equal(gW2, gW)
-            # what the reverse kernel's producer warp runs since the end of round 2 (ode_bwd_nn_p: the layered pass on the state
-            # chain, outer-product operands handed to the consumer warp): the one-piece adjoint's arithmetic in the same order
             xb3, gW3 = hc.ode_vjp_layered(m, X, u, lam)
             np.testing.assert_array_equal(xb3, xb)
             np.testing.assert_array_equal(gW3, gW)
