@@ -23,23 +23,22 @@ template <int BLOCK> __device__ __forceinline__ Scratch<BLOCK> scratch_col(int s
 }
 
 // ---- Bekker quadrature nodes as ONE non-inlined routine (four nodes per call, both arcs) ---------------------------------
-// Hand-off through kBekScratch scratch columns that follow the kFwdScratch forward columns:
-//   node parameters 0..12 | th 13..16 | sin 17..20 | cos 21..24 | fx 25..28 | fy 29..32 | fz 33..36
-constexpr int kBekScratch = 37;
-template <int BLOCK> __device__ __noinline__ void bekker_nodes4_call(int slot) {
-    const Scratch<BLOCK> S = scratch_col<BLOCK>(slot);
-    BekNodeParams q;
-    q.R = S[0]; q.n = S[1]; q.cos_end = S[2]; q.coef = S[3]; q.A = S[4]; q.om = S[5]; q.sin_tf = S[6]; q.B = S[7]; q.RomT = S[8]; q.C = S[9];
-    q.invK = S[10]; q.c_soil = S[11]; q.tan_phi = S[12];
-    double th[4], s[4], c[4], fx[4], fy[4], fz[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) { th[i] = S[13 + i]; s[i] = S[17 + i]; c[i] = S[21 + i]; }
-    bekker_nodes_vec<4>(q, th, s, c, fx, fy, fz);
-#pragma unroll
-    for (int i = 0; i < 4; i++) { S[25 + i] = fx[i]; S[29 + i] = fy[i]; S[33 + i] = fz[i]; }
+// Everything crosses the call BY VALUE: the 13 node parameters and (th, sin th, cos th) of the four nodes are register
+// arguments, the twelve integrand values come back as a returned struct — the device ABI keeps all 37 doubles in registers (no
+// local memory in the SASS).  Until the end of round 2 the hand-off went through 37 shared-memory scratch columns; the entry of
+// the routine then waited for its 25 LDS (5 % of the kernel's stall samples on that one line) and the caller re-read 12 results
+// per call: 44.6 -> 41.7 ms at 8192 x 100 rows, results bit-identical.
+constexpr int kBekScratch = 0;  // scratch columns of the hand-off (none any more; the margin columns follow kFwdScratch directly)
+struct BekOut12 { double fx[4], fy[4], fz[4]; };
+static __device__ __noinline__ BekOut12 bekker_nodes4_call(BekNodeParams q, double t0, double t1, double t2, double t3, double s0, double s1, double s2,
+                                                           double s3, double c0, double c1, double c2, double c3) {
+    const double th[4] = {t0, t1, t2, t3}, s[4] = {s0, s1, s2, s3}, c[4] = {c0, c1, c2, c3};
+    BekOut12 o;
+    bekker_nodes_vec<4>(q, th, s, c, o.fx, o.fy, o.fz);
+    return o;
 }
 // MARGIN: the diagnostic rollout keeps the per-lane minima of the kNumMargins branch margins in the scratch columns that
-// follow the node hand-off columns
+// follow the forward columns
 template <int BLOCK, bool MARGIN = false> struct BekNodesCall {
     int slot;
     __device__ __forceinline__ void margin(int kind, double v) const {
@@ -49,16 +48,12 @@ template <int BLOCK, bool MARGIN = false> struct BekNodesCall {
         }
     }
     __device__ __forceinline__ void operator()(const BekNodeParams& q, const double* th, const double* s, const double* c, double* fx, double* fy, double* fz) const {
-        const Scratch<BLOCK> S = scratch_col<BLOCK>(slot);
-        S[0] = q.R; S[1] = q.n; S[2] = q.cos_end; S[3] = q.coef; S[4] = q.A; S[5] = q.om; S[6] = q.sin_tf; S[7] = q.B; S[8] = q.RomT; S[9] = q.C;
-        S[10] = q.invK; S[11] = q.c_soil; S[12] = q.tan_phi;
 #pragma unroll
         for (int g = 0; g < 3; g++) {
+            const BekOut12 o = bekker_nodes4_call(q, th[4 * g], th[4 * g + 1], th[4 * g + 2], th[4 * g + 3], s[4 * g], s[4 * g + 1], s[4 * g + 2], s[4 * g + 3],
+                                                  c[4 * g], c[4 * g + 1], c[4 * g + 2], c[4 * g + 3]);
 #pragma unroll
-            for (int i = 0; i < 4; i++) { S[13 + i] = th[4 * g + i]; S[17 + i] = s[4 * g + i]; S[21 + i] = c[4 * g + i]; }
-            bekker_nodes4_call<BLOCK>(slot);
-#pragma unroll
-            for (int i = 0; i < 4; i++) { fx[4 * g + i] = S[25 + i]; fy[4 * g + i] = S[29 + i]; fz[4 * g + i] = S[33 + i]; }
+            for (int i = 0; i < 4; i++) { fx[4 * g + i] = o.fx[i]; fy[4 * g + i] = o.fy[i]; fz[4 * g + i] = o.fz[i]; }
         }
     }
 };
@@ -85,62 +80,56 @@ template <int TIRE, int TERR, int BLOCK, bool STORE_ACT, bool MARGIN = false> st
     }
 };
 
-// ---- fused forward stage (NN kernels): one non-inlined call = store the stage record, evaluate K = f(T), and apply the
-// RK4 stage update of HybridDynamics.cpp:470-500 (same arithmetic and order as rk4_fwd in avs_model.cuh), so that the
-// rolled loop in the kernel contains nothing but four calls.  Scratch slots: X 0 | ACC 13 | T 26 | INV 56.
+// ---- fused forward stage (forward-only NN kernels): one non-inlined call = evaluate K = f(T) and apply the RK4 stage update
+// of HybridDynamics.cpp:470-500 (same arithmetic and order as rk4_fwd in avs_model.cuh), so that the rolled loop in the kernel
+// contains nothing but four calls.  The stage input T crosses the call BY VALUE — 13 register arguments in, the next stage
+// input returned as a struct, which the device ABI keeps in registers — instead of through its scratch columns: the callee no
+// longer starts with 13 LDS and a wait for them (forward only 26.5 -> 25.3 ms at N = 4096 x 600 rows, 44.1 -> 41.6 ms at
+// N = 16 384 x 300; round 2, last session).  X and ACC stay in their columns (by value as well: 26.1 ms — they would be live
+// across the whole ODE evaluation).  Scratch slots: X 0 | ACC 13 | T 26 (written at the end of a step only) | INV 56.
 // tid = threadIdx.x, handed in by the caller: the non-inlined callee would otherwise re-read the special register (S2R, a
-// short-scoreboard wait at the head of every call: forward+store 11.25 -> 11.06 ms, round 2)
-template <int TERR, int BLOCK, bool STORE>
-__device__ __noinline__ void ode_fwd_stage_call(int tid, int lane0, double ul, double ur, int s, double* rec, double* act) {
+// short-scoreboard wait at the head of every call)
+struct St13 { double v[13]; };
+template <int TERR, int BLOCK>
+__device__ __noinline__ St13 ode_fwd_stage_call(St13 t, int tid, int lane0, double ul, double ur, int s) {
     const Scratch<BLOCK> X{g_smem + tid}, ACC{g_smem + 13 * BLOCK + tid}, T{g_smem + 26 * BLOCK + tid}, INV{g_smem + 56 * BLOCK + tid};
-    double x[13], k[13];
-#pragma unroll
-    for (int c = 0; c < 13; c++) x[c] = T[c];
-    if (STORE && rec) CkptSink::ckpt_store(rec, x, INV[0]);
-    ode_fwd<1, TIRE_NN, TERR, STORE>(c_mc, lane0, x, ul, ur, k, nullptr, ActOutPtr{act, kActPairStride});
+    double k[13];
+    ode_fwd<1, TIRE_NN, TERR, false>(c_mc, lane0, t.v, ul, ur, k, nullptr, ActOutPtr{nullptr, kActPairStride});
     const double h = kDt;
     double inv;
+    St13 o;
     if (s < 3) {
         const double wgt = (s == 0) ? 1.0 : 2.0;   // k1 + 2 k2 + 2 k3 + k4
         const double cs = (s == 2) ? h : .5 * h;   // X + .5h k1, X + .5h k2, X + h k3
 #pragma unroll
         for (int c = 0; c < 13; c++) {
             ACC[c] = (s == 0) ? fma(wgt, k[c], 0.0) : fma(wgt, k[c], ACC[c]);
-            x[c] = fma(cs, k[c], X[c]);
+            o.v[c] = fma(cs, k[c], X[c]);
         }
-        renorm(x, inv);
-#pragma unroll
-        for (int c = 0; c < 13; c++) T[c] = x[c];
+        renorm(o.v, inv);
     } else {
 #pragma unroll
-        for (int c = 0; c < 13; c++) x[c] = fma(h / 6.0, fma(1.0, k[c], ACC[c]), X[c]);
-        renorm(x, inv);
+        for (int c = 0; c < 13; c++) o.v[c] = fma(h / 6.0, fma(1.0, k[c], ACC[c]), X[c]);
+        renorm(o.v, inv);
 #pragma unroll
-        for (int c = 0; c < 13; c++) { X[c] = x[c]; T[c] = x[c]; }
+        for (int c = 0; c < 13; c++) { X[c] = o.v[c]; T[c] = o.v[c]; }
     }
     INV[0] = inv;
+    return o;
 }
-template <int TERR, int BLOCK, bool STORE> struct FusedStep {
+template <int TERR, int BLOCK> struct FusedStep {  // forward only; the instantiation that stores the adjoint's records uses FusedStepTiles
     const RolloutArgs& a;
     int n, lane0;
     bool writer;
     double ul, ur;
-    __device__ __forceinline__ void operator()(size_t step, double& inv_carry) const {
-        const size_t NK = (size_t)a.Nc;
-        const size_t rec_stride = ck_rec_stride(NK);
-        double* rec = (STORE && writer) ? a.ckpt + (step * 4) * rec_stride + ck_lane_offset(n) : nullptr;
-        // activation records: warp-tiled (avs_model.cuh, ActOutPtr); addressed by the thread's own global lane index, so
-        // tail lanes (which mirror the last vehicle) write into the padding of the last tile
-        const size_t act_stride = act_stage_doubles(NK);
-        double* act = STORE ? a.act + (step * 4) * act_stride + act_lane_offset((size_t)blockIdx.x * BLOCK + threadIdx.x) : nullptr;
+    __device__ __forceinline__ void operator()(size_t, double& inv_carry) const {
         const int tid = (int)threadIdx.x;
-        if (STORE) {
-            AVS_DBG_RANGE("state records of a step (store)", rec, 3 * rec_stride + 6 * kCkPairStride + 2, a.ckpt, a.ckpt_doubles);
-            AVS_DBG_RANGE("activation records of a step (store)", act, 3 * act_stride + 9 * kActPairStride + 2, a.act, a.act_doubles);
-        }
+        const Scratch<BLOCK> T = scratch_col<BLOCK>(26);
+        St13 t;
+#pragma unroll
+        for (int c = 0; c < 13; c++) t.v[c] = T[c];
 #pragma unroll 1
-        for (int s = 0; s < 4; s++)
-            ode_fwd_stage_call<TERR, BLOCK, STORE>(tid, lane0, ul, ur, s, rec ? rec + (size_t)s * rec_stride : nullptr, STORE ? act + (size_t)s * act_stride : nullptr);
+        for (int s = 0; s < 4; s++) t = ode_fwd_stage_call<TERR, BLOCK>(t, tid, lane0, ul, ur, s);
         inv_carry = scratch_col<BLOCK>(56)[0];
     }
 };

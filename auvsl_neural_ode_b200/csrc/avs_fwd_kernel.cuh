@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(kFwdBlock, (TIRE == TIRE_NN ? MINB * (128 / kF
                 for (int c = 0; c < 13; c++) S[26 + c] = __ldg(a.x0 + (size_t)live_to_ref(c) * N + n);
                 S[56] = 1.0;
             }
-            auto mk_step = [&a, n, lane0, writer](double ul, double ur) { return FusedStep<TERR, kFwdBlock, STORE>{a, n, lane0, writer, ul, ur}; };
+            auto mk_step = [&a, n, lane0, writer](double ul, double ur) { return FusedStep<TERR, kFwdBlock>{a, n, lane0, writer, ul, ur}; };
             rollout_fwd_body<STORE>(a, n, lane0, valid, S, mk_step);
         }
     } else {
