@@ -90,11 +90,12 @@ template <int TIRE, int TERR, int BLOCK, bool STORE_ACT, bool MARGIN = false> st
 // tid = threadIdx.x, handed in by the caller: the non-inlined callee would otherwise re-read the special register (S2R, a
 // short-scoreboard wait at the head of every call)
 struct St13 { double v[13]; };
-template <int TERR, int BLOCK>
+template <int TIRE, int TERR, int BLOCK, bool MARGIN = false>
 __device__ __noinline__ St13 ode_fwd_stage_call(St13 t, int tid, int lane0, double ul, double ur, int s) {
     const Scratch<BLOCK> X{g_smem + tid}, ACC{g_smem + 13 * BLOCK + tid}, T{g_smem + 26 * BLOCK + tid}, INV{g_smem + 56 * BLOCK + tid};
     double k[13];
-    ode_fwd<1, TIRE_NN, TERR, false>(c_mc, lane0, t.v, ul, ur, k, nullptr, ActOutPtr{nullptr, kActPairStride});
+    if (TIRE == TIRE_BEKKER) ode_fwd<1, TIRE, TERR, false, BekNodesCall<BLOCK, MARGIN>>(c_mc, lane0, t.v, ul, ur, k, nullptr, ActOutPtr{nullptr}, BekNodesCall<BLOCK, MARGIN>{kFwdScratch});
+    else ode_fwd<1, TIRE, TERR, false>(c_mc, lane0, t.v, ul, ur, k, nullptr, ActOutPtr{nullptr, kActPairStride});
     const double h = kDt;
     double inv;
     St13 o;
@@ -117,7 +118,7 @@ __device__ __noinline__ St13 ode_fwd_stage_call(St13 t, int tid, int lane0, doub
     INV[0] = inv;
     return o;
 }
-template <int TERR, int BLOCK> struct FusedStep {  // forward only; the instantiation that stores the adjoint's records uses FusedStepTiles
+template <int TIRE, int TERR, int BLOCK, bool MARGIN = false> struct FusedStep {  // forward only; the instantiation that stores the adjoint's records uses FusedStepTiles
     const RolloutArgs& a;
     int n, lane0;
     bool writer;
@@ -129,7 +130,7 @@ template <int TERR, int BLOCK> struct FusedStep {  // forward only; the instanti
 #pragma unroll
         for (int c = 0; c < 13; c++) t.v[c] = T[c];
 #pragma unroll 1
-        for (int s = 0; s < 4; s++) t = ode_fwd_stage_call<TERR, BLOCK>(t, tid, lane0, ul, ur, s);
+        for (int s = 0; s < 4; s++) t = ode_fwd_stage_call<TIRE, TERR, BLOCK, MARGIN>(t, tid, lane0, ul, ur, s);
         inv_carry = scratch_col<BLOCK>(56)[0];
     }
 };

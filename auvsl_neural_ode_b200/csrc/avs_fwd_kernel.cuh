@@ -44,20 +44,24 @@ __global__ void __launch_bounds__(kFwdBlock, (TIRE == TIRE_NN ? MINB * (128 / kF
                 for (int c = 0; c < 13; c++) S[26 + c] = __ldg(a.x0 + (size_t)live_to_ref(c) * N + n);
                 S[56] = 1.0;
             }
-            auto mk_step = [&a, n, lane0, writer](double ul, double ur) { return FusedStep<TERR, kFwdBlock>{a, n, lane0, writer, ul, ur}; };
+            auto mk_step = [&a, n, lane0, writer](double ul, double ur) { return FusedStep<TIRE_NN, TERR, kFwdBlock>{a, n, lane0, writer, ul, ur}; };
             rollout_fwd_body<STORE>(a, n, lane0, valid, S, mk_step);
         }
     } else {
-        const size_t stage_stride = (size_t)4 * a.Nc * kActLen;
         const Scratch<kFwdBlock> M = scratch_col<kFwdBlock>(kFwdScratch + kBekScratch);
         if (MARGIN) {
 #pragma unroll
             for (int k = 0; k < kNumMargins; k++) M[k] = 1e300;
         }
-        auto mk_step = [&a, n, lane0, writer, S, stage_stride](double ul, double ur) {
-            typedef OdeFwdCall<TIRE, TERR, kFwdBlock, false, MARGIN> Ode;
-            return GenericStep<false, Ode, Scratch<kFwdBlock>>{Ode{lane0, 26, 39, ul, ur, nullptr, stage_stride}, a, n, lane0, writer, S};
-        };
+        // fused stages with the stage input by value, as in the forward-only NN branch (through GenericStep / OdeFwdCall on the
+        // T and K scratch columns: 41.7 against 40.9 ms at 8192 x 100 rows): T starts as a copy of X, the carried inverse norm as 1
+        {
+            const size_t N = (size_t)a.N;
+#pragma unroll
+            for (int c = 0; c < 13; c++) S[26 + c] = __ldg(a.x0 + (size_t)live_to_ref(c) * N + n);
+            S[56] = 1.0;
+        }
+        auto mk_step = [&a, n, lane0, writer](double ul, double ur) { return FusedStep<TIRE, TERR, kFwdBlock, MARGIN>{a, n, lane0, writer, ul, ur}; };
         rollout_fwd_body<false>(a, n, lane0, valid, S, mk_step);
         if (MARGIN) {  // minimum over the four wheel lanes of the vehicle
 #pragma unroll
