@@ -62,7 +62,14 @@ template <int REGION> AVS_HD Bek3 bekker_node(const BekkerCtx& k, double th) {
 }
 
 // BekkerTireModel::integrate (:163-179) for the three force integrands of one region at once
+// On the device this scalar walk is the COLD path (degenerate arcs, the centre arc when the ground pressure saturates): kept out
+// of line, so that its ~30 inlined libm calls per region do not sit between the hot blocks of the stage (rollout kernel 41.0 ->
+// 40.5 ms at 8192 x 100 rows; with the context passed by value instead of by reference: 40.9)
+#if defined(__CUDACC__)
+template <int REGION> __host__ __device__ __noinline__ Bek3 bekker_integrate(const BekkerCtx& k, double upper_b, double lower_b) {
+#else
 template <int REGION> AVS_HD Bek3 bekker_integrate(const BekkerCtx& k, double upper_b, double lower_b) {
+#endif
     const double dtheta = (upper_b - lower_b) / 10.0;
     const double eps = dtheta * .1;
     Bek3 sum = {0.0, 0.0, 0.0};
