@@ -8,6 +8,8 @@
 #include <iostream>
 #include <random>
 #include <string>
+#include <vector>
+#include <algorithm>
 
 #include "TestTerrainMaps.h"
 #include "Trainer.h"
@@ -69,6 +71,39 @@ int main(int argc, char** argv) {
         double sum = 0, wsum = 0;
         for (size_t i = 0; i < train.m_params.size(); i++) { sum += train.m_params[i]; wsum += (double)(i + 1) * train.m_params[i]; }
         std::cout << "params sum " << sum << " weighted " << wsum << " p[0] " << train.m_params[0] << " p[103] " << train.m_params[103] << "\n";
+    }
+    {   // regression (round-1 advice): parameters set on the host after a device-side optimiser step must win, and a step taken
+        // through one handle must survive another handle re-binding the shared context
+        auto a = factory->makeSystem(), b = factory->makeSystem();
+        const int np = a->getNumParams();
+        System<ADF>::VectorS p0(np), stepped(np), again(np), custom(np), back(np);
+        a->getParams(p0);
+        std::vector<double> red(np + 2, 0.0);
+        for (int i = 0; i < 104; i++) red[i] = 0.5 * ((i % 7) - 3);
+        red[np + 1] = 1.0;  // n_kept
+        a->applyRmsProp(red.data(), 1e-3, 0.0);
+        a->getParams(stepped);
+        b->setParams(p0);       // another handle takes the context over ...
+        b->getParams(again);
+        a->getParams(again);    // ... and the step taken through `a` is still there
+        custom = stepped;
+        custom[0] += 0.125;
+        a->setParams(custom);   // host parameters after a device step: must not be ignored
+        a->getParams(back);
+        bool ok = stepped[1] != p0[1] && stepped[104] == p0[104];
+        for (int i = 0; i < np; i++) ok = ok && again[i] == stepped[i] && back[i] == custom[i];
+        // and they are the ones the device evaluates with: a forward evaluation differs from the one with the stepped set
+        System<ADF>::VectorS X(23), Xd1(23), Xd2(23);
+        a->getDefaultInitialState(X);
+        X[17] = X[19] = 4.0; X[18] = X[20] = 3.0; X[21] = 4.0; X[22] = 3.0;
+        a->forward(X, Xd1);
+        a->setParams(stepped);
+        a->forward(X, Xd2);
+        double dmax = 0;
+        for (int i = 0; i < 21; i++) dmax = std::max(dmax, std::fabs(Xd1[i] - Xd2[i]));
+        ok = ok && dmax > 0;
+        std::cout << "parameter hand-over check: " << (ok ? "OK" : "FAILED") << " (|dXd| " << dmax << ")\n";
+        if (!ok) return 3;
     }
     std::cout << "synth_demo OK\n";
     return 0;

@@ -32,6 +32,7 @@ def test_synth_demo_runs_and_matches_python_path(tmp_path):
     out = subprocess.run([os.path.join(HOST, "examples", "synth_demo"), d], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "synth_demo OK" in out.stdout
+    assert "parameter hand-over check: OK" in out.stdout  # setParams after a device step wins; a step survives another handle's re-bind
     ld3 = float(re.search(r"LD3 avg loss: ([-+0-9.eE]+)", out.stdout).group(1))
     assert np.isfinite(ld3) and 0 < ld3 < 10
     avg = [float(x) for x in re.findall(r"Avg Loss: ([-+0-9.eE]+)", out.stdout)]
