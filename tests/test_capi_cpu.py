@@ -66,3 +66,13 @@ def test_legacy_net_csv_parser_handles_the_reference_file_quirks():
     import pytest
     with pytest.raises(capi.AvsError):
         capi.load_legacy_net_csv(os.path.join(here, "golden", "legacy_net_like.npy"))
+
+
+def test_committed_counters_belong_to_the_committed_kernel_sources():
+    """bench.py builds its roofline blocks from profiles/r2_counters.json; the capture must be of THIS csrc/ (a kernel change
+    without a fresh ncu capture would otherwise go unnoticed until `counters.matches_build` shows false on the GPU box)"""
+    import json
+    import bench
+    c = json.load(open(os.path.join(ROOT, "profiles", "r2_counters.json")))
+    assert c["source_hash"] == bench.source_hash()
+    assert {"rollout_fwd_kernel<NN,flat,STORE>", "rollout_bwd2_kernel<flat>", "rollout_fwd_kernel<NN,flat>", "rollout_fwd_kernel<Bekker,dyn>"} <= set(c["kernels"])
