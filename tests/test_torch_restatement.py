@@ -111,6 +111,95 @@ def test_live_restatement_matches_fixture_and_oracle():
         assert abs(fd - g[k]) <= 1e-6 * max(1e-3, abs(g).max()), (k, fd, g[k])
 
 
+# ---- Bekker tire model: independent numpy restatement (tests/bekker_restatement.py: whole arcs as numpy expressions) ----------------
+def _bekker_cases(n=300, seed=5):
+    rng = np.random.default_rng(seed)
+    for i in range(n):
+        zr = rng.uniform(1e-4, 0.03) if i % 10 else rng.uniform(0.03, 0.12)  # every tenth: saturated ground pressure / zr > R
+        soil = np.array([29.76 * rng.uniform(.8, 1.2), 2083 * rng.uniform(.8, 1.2), 0.8 * rng.uniform(.8, 1.2), rng.uniform(0, .1), .3927 * rng.uniform(.8, 1.2)])
+        yield [zr, rng.uniform(-1, 1.5), rng.uniform(-0.5, 0.5), 0.098 * rng.uniform(-4, 12)], soil
+
+
+def test_bekker_tire_forces_vs_numpy_restatement():
+    import bekker_restatement as br
+    from oracle import pyref
+    have_ref = pyref.available()
+    worst_o = worst_r = 0.0
+    for inp, soil in _bekker_cases():
+        want = np.array(br.get_forces(*br.get_features(*inp), *soil))
+        feat, f = po.bekker_forces(inp, soil)
+        assert np.allclose(feat[1:], br.get_features(*inp)[1:], rtol=0, atol=1e-15)
+        worst_o = max(worst_o, rel(f[:3], want))
+        if have_ref:
+            _, fr = pyref.bekker_forces(inp, soil)
+            worst_r = max(worst_r, rel(np.asarray(fr)[:3], want))
+    print(f"Bekker get_forces vs numpy restatement: oracle {worst_o:.2e}, reference library {worst_r:.2e}" + ("" if have_ref else " (not built here)"))
+    assert worst_o < 1e-11 and worst_r < 1e-11
+
+
+def _bekker_short_rollout():
+    import torch
+
+    import torch_restatement as tr
+    from auvsl_neural_ode_b200 import synth
+    PB = po.bekker_default_params()
+    fn = tr.bekker_wheel_forces(PB)
+    x0, ctrl, _ = synth.make_batch(3, 4, seed=5, z_stable=0.065)
+    ctrl = np.clip(ctrl, 0.5, 8.0)
+    with torch.no_grad():
+        Xt = torch.tensor(x0).T.contiguous()
+        for i in range(3):
+            Xt = tr.macro_step(None, Xt, torch.tensor(ctrl[i]).T, "flat", 10, fn)
+    return PB, fn, x0, ctrl, Xt.numpy().T
+
+
+def test_bekker_ode_and_rollout_vs_independent_restatements():
+    """dense-algebra ODE (torch) around the numpy Bekker model against the oracle and the CPU build of the device math"""
+    import torch
+
+    import torch_restatement as tr
+    PB, fn, x0, ctrl, xf_want = _bekker_short_rollout()
+    worst_o = worst_h = 0.0
+    for terr in ("flat", "slope"):
+        X, U = (T_["ode_X"] if terr == "flat" else T_["ode_X_slope"]), T_["ode_U"]
+        with torch.no_grad():
+            Xd = tr.ode(None, torch.tensor(X), torch.tensor(U), terr, fn).numpy()
+        assert np.abs(Xd[:, 11:17]).max() > 100.0  # wheels in the soil: the Bekker forces dominate the accelerations
+        m = hc.model(1, TERR[terr], PB)
+        for i in range(X.shape[0]):
+            worst_o = max(worst_o, rel(po.ode(1, PB, po.terrain(TERR[terr]), X[i], U[i]), Xd[i]))
+            worst_h = max(worst_h, rel(hc.ode(m, X[i][hc.LIVE], U[i], X[i][17:21]), Xd[i][hc.LIVE]))
+    _, xf_o = po.rollout_batch(1, PB, po.terrain(0), x0, ctrl, 4)
+    _, xf_h = hc.rollout(hc.model(1, 0, PB), x0, ctrl, 4, want_list=False)
+    eo, eh = rel(xf_o, xf_want), rel(xf_h[hc.LIVE] if xf_h.shape[0] == 21 else xf_h, xf_want[hc.LIVE] if xf_h.shape[0] == 21 else xf_want)
+    print(f"Bekker ODE: oracle {worst_o:.2e}, device math (CPU build) {worst_h:.2e}; 30 RK4 steps: oracle {eo:.2e}, device math {eh:.2e}")
+    assert worst_o < 1e-11 and worst_h < 1e-9 and eo < 1e-11 and eh < 1e-9
+
+
+@pytest.mark.gpu
+def test_cuda_bekker_path_vs_independent_restatements():
+    import torch
+
+    import torch_restatement as tr
+    from auvsl_neural_ode_b200 import capi
+    PB, fn, x0, ctrl, xf_want = _bekker_short_rollout()
+    ctx = capi.Context(0, capi.TIRE_BEKKER)
+    ctx.set_bekker_params(PB)
+    report = {}
+    for terr in ("flat", "slope"):
+        ctx.set_terrain(capi.FLAT if terr == "flat" else capi.SLOPE)
+        X, U = (T_["ode_X"] if terr == "flat" else T_["ode_X_slope"]), T_["ode_U"]
+        with torch.no_grad():
+            Xd = tr.ode(None, torch.tensor(X), torch.tensor(U), terr, fn).numpy()
+        report[f"ode {terr}"] = rel(ctx.ode(X.T.copy(), U.T.copy()).T, Xd)
+    ctx.set_terrain(capi.FLAT)
+    _, xf = ctx.rollout(x0, ctrl, 4, want_list=False)
+    report["30 RK4 steps"] = rel(xf, xf_want)
+    print("CUDA Bekker path vs numpy / torch restatements:", {k: f"{v:.2e}" for k, v in report.items()})
+    for k, v in report.items():
+        assert v < 1e-9, (k, v)
+
+
 @pytest.mark.gpu
 def test_cuda_path_vs_torch_autograd():
     """the CUDA path through the C ABI against the independent torch numbers: ODE values, every row of a 10-macro-step

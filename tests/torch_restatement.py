@@ -141,8 +141,22 @@ def tire_net(p104, vx, vy, wheel_w, sink):
 
 
 # ---- A3 + A4: one ODE evaluation ------------------------------------------------------------------------------------------------
-def ode(p104, X, u, terrain="flat"):
-    """X [N,21], u [N,2] -> Xd [N,21]"""
+def bekker_wheel_forces(p5):
+    """tire function for ode(): the Bekker model of tests/bekker_restatement.py (numpy, values only — the reference's Bekker
+    gradient is not finite, so there is nothing to differentiate against)"""
+    import bekker_restatement as br
+
+    def fn(sink, cv, wheel_w):
+        out = np.zeros((sink.shape[0], 3))
+        for n in range(sink.shape[0]):
+            out[n] = br.wheel_force(p5, float(sink[n]), float(cv[n, 0]), float(cv[n, 1]), float(cv[n, 2]), float(wheel_w[n]))
+        t = torch.tensor(out, dtype=F64)
+        return t[:, 0], t[:, 1], t[:, 2]
+    return fn
+
+
+def ode(p104, X, u, terrain="flat", tire_fn=None):
+    """X [N,21], u [N,2] -> Xd [N,21]; tire_fn(sink, cv, wheel_w) -> (Fx, Fy, Fz incl. damping) replaces the tire network"""
     N = X.shape[0]
     q, pos, w, v = X[:, 0:4], X[:, 4:7], X[:, 11:14], X[:, 14:17]
     qd = torch.stack([u[:, 0], u[:, 1], u[:, 0], u[:, 1]], 1)
@@ -154,8 +168,11 @@ def ode(p104, X, u, terrain="flat"):
         cp = (Rm @ e) + pos
         sink = altitude(terrain, cp[:, 0], cp[:, 1]) - cp[:, 2]
         cv = v + torch.cross(w, e.expand(N, 3), dim=1)  # v - skew(e) w
-        fx, fy, fz = tire_net(p104, cv[:, 0], cv[:, 1], X[:, 17 + i], sink)
-        fz = fz + (-20.0) * cv[:, 2]
+        if tire_fn is None:
+            fx, fy, fz = tire_net(p104, cv[:, 0], cv[:, 1], X[:, 17 + i], sink)
+            fz = fz + (-20.0) * cv[:, 2]
+        else:
+            fx, fy, fz = tire_fn(sink, cv, X[:, 17 + i])
         zero = torch.zeros_like(fx)
         fext = torch.stack([zero, zero, zero, fx, -fz, fy], 1)
         vi = vb @ X_W[i].T
@@ -180,18 +197,18 @@ def _renorm(X):
     return torch.cat([X[:, :4] / X[:, :4].norm(dim=1, keepdim=True), X[:, 4:]], 1)
 
 
-def rk4(p104, X, u, terrain="flat"):
-    k1 = ode(p104, X, u, terrain)
-    k2 = ode(p104, _renorm(X + 0.5 * DT * k1), u, terrain)
-    k3 = ode(p104, _renorm(X + 0.5 * DT * k2), u, terrain)
-    k4 = ode(p104, _renorm(X + DT * k3), u, terrain)
+def rk4(p104, X, u, terrain="flat", tire_fn=None):
+    k1 = ode(p104, X, u, terrain, tire_fn)
+    k2 = ode(p104, _renorm(X + 0.5 * DT * k1), u, terrain, tire_fn)
+    k3 = ode(p104, _renorm(X + 0.5 * DT * k2), u, terrain, tire_fn)
+    k4 = ode(p104, _renorm(X + DT * k3), u, terrain, tire_fn)
     return _renorm(X + (DT / 6.0) * (k1 + 2 * k2 + 2 * k3 + k4))
 
 
-def macro_step(p104, X, u, terrain="flat", substeps=10):
+def macro_step(p104, X, u, terrain="flat", substeps=10, tire_fn=None):
     for _ in range(substeps):
         X = torch.cat([X[:, :17], u[:, 0:1], u[:, 1:2], u[:, 0:1], u[:, 1:2]], 1)
-        X = rk4(p104, X, u, terrain)
+        X = rk4(p104, X, u, terrain, tire_fn)
     return X
 
 
